@@ -1,0 +1,166 @@
+/*
+ * metran_b200.h -- C ABI of libmetran_b200.so: batched sequential-processing Kalman
+ * filter, innovation log-likelihood and RTS smoother for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the Kalman hot path of pastas/metran.  Every entry
+ * point replaces one reference interface (file:line relative to the reference tree):
+ *
+ *   mkf_filter_history   <- seqkalmanfilter(...)            metran/kalmanfilter.py:236-400
+ *                            (the 9-in / 7-out `filtermethod` plug-in point selected by
+ *                             SPKalmanFilter.__init__/run_filter, :494-504, :729-771)
+ *   mkf_filter_loglik    <- run_filter() + get_mle(warmup)   metran/kalmanfilter.py:696-778, 550-567
+ *                            (what Metran.get_mle / BaseSolver.objfunction consume,
+ *                             metran/metran.py:605-622, metran/solver.py:42-63)
+ *   mkf_dfm_loglik       <- same, for Metran-shaped models   metran/metran.py:265-416
+ *                            (A, Q diagonal; H = [I | loadings]; quirk Q13 of SURVEY.md)
+ *   mkf_dfm_loglik_alpha <- Metran._get_matrices + the above metran/metran.py:246-416, 605-622
+ *                            (parameter vector alpha -> phi, q on the device)
+ *   mkf_smoother         <- kalmansmoother(...)              metran/kalmanfilter.py:403-476
+ *   mkf_project          <- SPKalmanFilter.simulate()        metran/kalmanfilter.py:569-603
+ *   mkf_reduce_sum       <- the pooled objective handed to NCCL all-reduce (new; the
+ *                            reference has no multi-device path)
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers to IEEE fp64 (double) unless noted; layouts
+ *     are model-major and C-contiguous: y[B][T][m], A[B][n][n], H[B][m][n], fc[B][T][n][n].
+ *   - A `*_stride` argument is the distance IN ELEMENTS between consecutive models;
+ *     0 shares one array between all models of the batch (e.g. one observation matrix
+ *     for 8192 parameter draws).
+ *   - Observations are NaN-coded: a slot is "missing" when it is not finite or equals
+ *     -1e10 exactly, the rule of SPKalmanFilter.set_observations (kalmanfilter.py:657,
+ *     666-667).  Observed series of a time step are processed in ascending index order,
+ *     the order set_observations produces (kalmanfilter.py:667-674).
+ *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and return an int code; nothing throws across the boundary.
+ *     Inputs are borrowed for the duration of the enqueued work, outputs are caller-owned.
+ *   - Numerical failure follows the reference: NaN/inf propagate into the outputs
+ *     (kalmanfilter.py:378 takes log of whatever f is); additionally status[b] gets
+ *     MKF_STATUS_* bits so a caller can tell.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point
+ *     returns MKF_ERR_CUDA.
+ */
+#ifndef METRAN_B200_H
+#define METRAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKF_VERSION 100 /* 0.1.0 */
+
+/* return codes */
+#define MKF_OK 0
+#define MKF_ERR_BAD_ARG 1     /* NULL pointer, non-positive size, bad stride */
+#define MKF_ERR_UNSUPPORTED 2 /* shape outside the compiled kernels (see mkf_limits) */
+#define MKF_ERR_CUDA 3        /* CUDA runtime error; see mkf_last_cuda_error() */
+
+/* per-model status bits (int32) */
+#define MKF_STATUS_NONPOSITIVE_F 1 /* an innovation variance f <= 0 or non-finite */
+#define MKF_STATUS_CHOL_FAILED 2   /* smoother: predicted covariance not positive definite */
+
+/* flags */
+#define MKF_FLAG_A_DIAGONAL 1 /* caller guarantees A is diagonal (Metran: always)  */
+#define MKF_FLAG_Q_DIAGONAL 2 /* caller guarantees Q is diagonal (Metran: always)  */
+
+int mkf_version(void);
+const char *mkf_error_string(int code);
+const char *mkf_last_cuda_error(void);
+/* n_max: largest state dimension of the generic kernels; dfm_m_max / dfm_k_max: largest
+ * series / common-factor counts of the thread-per-model DFM kernels. */
+void mkf_limits(int32_t *n_max, int32_t *dfm_m_max, int32_t *dfm_k_max);
+
+/*
+ * Forward filter with the full reference result contract (kalmanfilter.py:392-400).
+ *   y[B][T][m]; A,Q[B][n][n]; H[B][m][n]; R[B][m]; x0[B][n] (NULL -> 0); P0[B][n][n]
+ *   (NULL -> I), the defaults of run_filter (kalmanfilter.py:747-750).
+ * The covariance predict uses diag(A) only, the mean predict the full A
+ * (kalmanfilter.py:318-331).
+ * Outputs (any history pointer may be NULL to skip it):
+ *   sigma[B][T], detf[B][T]: per-step sum v^2/f and sum log f, 0 on steps without
+ *     observation; cnt[B][T] (int32): observed-series count.  The reference's compacted
+ *     `sigmas[:sigmacount]` is sigma[cnt > 0] (kalmanfilter.py:380-382).
+ *   fm[B][T][n], fc[B][T][n][n], pm, pc: filtered / predicted means and covariances.
+ *   mle[B], nobs[B] (int64), status[B] (int32): -2 log L with `warmup` semantics of
+ *     get_mle (kalmanfilter.py:563-566): the first `warmup` OBSERVED steps are dropped
+ *     from the sums, nobs counts observations of raw time steps t >= warmup.
+ */
+int mkf_filter_history(int64_t B, int64_t T, int32_t n, int32_t m,
+                       const double *y, int64_t y_stride,
+                       const double *A, int64_t A_stride,
+                       const double *Q, int64_t Q_stride,
+                       const double *H, int64_t H_stride,
+                       const double *R, int64_t R_stride,
+                       const double *x0, int64_t x0_stride,
+                       const double *P0, int64_t P0_stride,
+                       int32_t warmup, uint32_t flags,
+                       double *sigma, double *detf, int32_t *cnt,
+                       double *fm, double *fc, double *pm, double *pc,
+                       double *mle, int64_t *nobs, int32_t *status, void *stream);
+
+/* Same recursion, -2 log L only (no history traffic). */
+int mkf_filter_loglik(int64_t B, int64_t T, int32_t n, int32_t m,
+                      const double *y, int64_t y_stride,
+                      const double *A, int64_t A_stride,
+                      const double *Q, int64_t Q_stride,
+                      const double *H, int64_t H_stride,
+                      const double *R, int64_t R_stride,
+                      const double *x0, int64_t x0_stride,
+                      const double *P0, int64_t P0_stride,
+                      int32_t warmup, uint32_t flags,
+                      double *mle, int64_t *nobs, int32_t *status, void *stream);
+
+/*
+ * Metran-shaped dynamic factor model, one thread per model: n = m + k states,
+ * A = diag(phi[n]), Q = diag(q[n]), H = [I_m | gamma[m][k]], R = r[m] (NULL -> 0),
+ * x0 = 0, P0 = I (metran.py:283-384, kalmanfilter.py:747-750).
+ */
+int mkf_dfm_loglik(int64_t B, int64_t T, int32_t m, int32_t k,
+                   const double *y, int64_t y_stride,
+                   const double *phi, int64_t phi_stride,
+                   const double *q, int64_t q_stride,
+                   const double *gamma, int64_t gamma_stride,
+                   const double *r, int64_t r_stride,
+                   int32_t warmup,
+                   double *mle, int64_t *nobs, int32_t *status, void *stream);
+
+/*
+ * As mkf_dfm_loglik with the parameter -> matrix map of Metran fused in front:
+ * phi_i = exp(-dt / alpha_i) (metran.py:262-263); q_i = (1 - phi_i^2)(1 - comm_i) for
+ * the m specific factors, comm_i = sum_j gamma[i][j]^2, and 1 - phi_i^2 for the k common
+ * factors (metran.py:310-322).  alpha[B][m+k] in state order (series, then common).
+ */
+int mkf_dfm_loglik_alpha(int64_t B, int64_t T, int32_t m, int32_t k,
+                         const double *y, int64_t y_stride,
+                         const double *alpha, int64_t alpha_stride, double dt,
+                         const double *gamma, int64_t gamma_stride,
+                         int32_t warmup,
+                         double *mle, int64_t *nobs, int32_t *status, void *stream);
+
+/*
+ * RTS smoother (kalmanfilter.py:453-474): G_t = P_f[t] A^T P_p[t+1]^-1 (solved by
+ * Cholesky; the reference uses pinv), x_s[t] = x_f[t] + G_t (x_s[t+1] - x_p[t+1]),
+ * P_s[t] = P_f[t] + G_t (P_s[t+1] - P_p[t+1]) G_t^T.  sm[B][T][n], sc[B][T][n][n].
+ */
+int mkf_smoother(int64_t B, int64_t T, int32_t n,
+                 const double *fm, const double *fc, const double *pm, const double *pc,
+                 const double *A, int64_t A_stride, uint32_t flags,
+                 double *sm, double *sc, int32_t *status, void *stream);
+
+/*
+ * Projection of state moments (kalmanfilter.py:596-602): means_out[B][T][p] = Hp x_t,
+ * var_out[B][T][p] = max(diag(Hp P_t Hp^T), 0); Hp[B][p][n].
+ */
+int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p,
+                const double *means, const double *covs,
+                const double *Hp, int64_t Hp_stride,
+                double *means_out, double *var_out, void *stream);
+
+/* Deterministic (fixed-tree) sum of v[0..count) into out[0]; feeds the all-reduce. */
+int mkf_reduce_sum(const double *v, int64_t count, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METRAN_B200_H */

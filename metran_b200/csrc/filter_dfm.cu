@@ -1,0 +1,58 @@
+// C-ABI entry points of the thread-per-model DFM filter (see filter_dfm.cuh).
+#include "filter_dfm.cuh"
+
+namespace mkf_dfm {
+template <> int launch_for_m<0>(int, const DfmArgs &, cudaStream_t);
+template <> int launch_for_m<1>(int, const DfmArgs &, cudaStream_t);
+template <> int launch_for_m<2>(int, const DfmArgs &, cudaStream_t);
+template <> int launch_for_m<3>(int, const DfmArgs &, cudaStream_t);
+
+static int run(int m, int k, DfmArgs &a, cudaStream_t s) {
+    if (a.B < 0 || a.T < 0 || m <= 0 || k < 0) return MKF_ERR_BAD_ARG;
+    if (!a.y || !a.mle || (k > 0 && !a.gamma)) return MKF_ERR_BAD_ARG;
+    if (m > kMaxM || k > kMaxK) return MKF_ERR_UNSUPPORTED;
+    if (a.B == 0) return MKF_OK;
+    // bulk (TMA) staging needs every model row 16-byte aligned
+    a.use_bulk = ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && ((a.y_stride & 1) == 0);
+    switch (k) {
+        case 0: return launch_for_m<0>(m, a, s);
+        case 1: return launch_for_m<1>(m, a, s);
+        case 2: return launch_for_m<2>(m, a, s);
+        case 3: return launch_for_m<3>(m, a, s);
+    }
+    return MKF_ERR_UNSUPPORTED;
+}
+}  // namespace mkf_dfm
+
+extern "C" int mkf_dfm_loglik(int64_t B, int64_t T, int32_t m, int32_t k, const double *y, int64_t y_stride,
+                              const double *phi, int64_t phi_stride, const double *q, int64_t q_stride,
+                              const double *gamma, int64_t gamma_stride, const double *r, int64_t r_stride,
+                              int32_t warmup, double *mle, int64_t *nobs, int32_t *status, void *stream) {
+    if (!phi || !q) return MKF_ERR_BAD_ARG;
+    mkf_dfm::DfmArgs a{};
+    a.B = B; a.T = T; a.y = y; a.y_stride = y_stride;
+    a.phi = phi; a.phi_stride = phi_stride; a.q = q; a.q_stride = q_stride;
+    a.gamma = gamma; a.gamma_stride = gamma_stride; a.r = r; a.r_stride = r_stride;
+    a.alpha = nullptr; a.dt = 1.0; a.warmup = warmup;
+    a.mle = mle; a.nobs = nobs; a.status = status;
+    return mkf_dfm::run(m, k, a, (cudaStream_t)stream);
+}
+
+extern "C" int mkf_dfm_loglik_alpha(int64_t B, int64_t T, int32_t m, int32_t k, const double *y,
+                                    int64_t y_stride, const double *alpha, int64_t alpha_stride, double dt,
+                                    const double *gamma, int64_t gamma_stride, int32_t warmup, double *mle,
+                                    int64_t *nobs, int32_t *status, void *stream) {
+    if (!alpha) return MKF_ERR_BAD_ARG;
+    mkf_dfm::DfmArgs a{};
+    a.B = B; a.T = T; a.y = y; a.y_stride = y_stride;
+    a.gamma = gamma; a.gamma_stride = gamma_stride;
+    a.alpha = alpha; a.alpha_stride = alpha_stride; a.dt = dt; a.warmup = warmup;
+    a.mle = mle; a.nobs = nobs; a.status = status;
+    return mkf_dfm::run(m, k, a, (cudaStream_t)stream);
+}
+
+extern "C" void mkf_limits(int32_t *n_max, int32_t *dfm_m_max, int32_t *dfm_k_max) {
+    if (n_max) *n_max = 32;
+    if (dfm_m_max) *dfm_m_max = mkf_dfm::kMaxM;
+    if (dfm_k_max) *dfm_k_max = mkf_dfm::kMaxK;
+}

@@ -1,0 +1,23 @@
+// Instantiates the thread-per-model DFM kernels for K = 1 common factors, M = 1..8 series.
+#include "filter_dfm.cuh"
+
+namespace mkf_dfm {
+template <>
+int launch_for_m<1>(int m, const DfmArgs &a, cudaStream_t s) {
+    switch (m) {
+#ifdef MKF_DFM_ONLY_M5
+        case 5: return launch<5, 1>(a, s);
+#else
+        case 1: return launch<1, 1>(a, s);
+        case 2: return launch<2, 1>(a, s);
+        case 3: return launch<3, 1>(a, s);
+        case 4: return launch<4, 1>(a, s);
+        case 5: return launch<5, 1>(a, s);
+        case 6: return launch<6, 1>(a, s);
+        case 7: return launch<7, 1>(a, s);
+        case 8: return launch<8, 1>(a, s);
+#endif
+        default: return MKF_ERR_UNSUPPORTED;
+    }
+}
+}  // namespace mkf_dfm

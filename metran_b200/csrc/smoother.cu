@@ -1,0 +1,313 @@
+// Batched Rauch-Tung-Striebel smoother and state projections (n <= 32).
+//
+// mkf_smoother replaces kalmansmoother (reference metran/kalmanfilter.py:403-476):
+//   G_t    = P_f[t] A^T P_p[t+1]^-1
+//   x_s[t] = x_f[t] + G_t (x_s[t+1] - x_p[t+1])
+//   P_s[t] = P_f[t] + G_t (P_s[t+1] - P_p[t+1]) G_t^T
+// The reference forms pinv(P_p[t+1]) by SVD (:455); P_p = A P A^T + Q is symmetric
+// positive definite for every Metran model (q_i > 0), so this kernel solves
+// P_p G^T = A P_f with a Cholesky factorisation instead (cond(P_p) <= ~1e2 on
+// Metran-like models, SURVEY.md s7: the two agree to ~1e-14).
+//
+// Mapping: NP = 4/8/16/32 lanes per model, lane r owns row r.  Per backward step
+//   1. right-looking Cholesky of P_p, one column per iteration, column broadcast through
+//      shared memory;
+//   2. lane c solves L L^T g = (A P_f)[:,c] entirely in registers with L broadcast from
+//      shared memory -> lane c holds row c of G;
+//   3. two n x n x n products with the shared-memory operand broadcast to all lanes.
+// Covariances are read/written column-per-lane (coalesced); they are symmetric up to
+// rounding, see filter_generic.cu.
+//
+// mkf_project replaces the per-time-step Python loop of SPKalmanFilter.simulate
+// (metran/kalmanfilter.py:596-602).
+#include "mkf_common.cuh"
+
+namespace {
+
+using namespace mkf;
+
+struct SmootherArgs {
+    int64_t B, T;
+    int n;
+    const double *fm, *fc, *pm, *pc, *A;
+    int64_t A_stride;
+    unsigned flags;
+    double *sm, *sc;
+    int32_t *status;
+    int smem_model;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int LD = NP + 2;  // padded leading dimension (even: rows stay double2-aligned)
+    const int n = a.n;
+    const int group_in_block = threadIdx.x / NP;
+    const int r = threadIdx.x % NP;
+    const int group_in_warp = (threadIdx.x & 31) / NP;
+    const unsigned gmask = (NP == 32) ? 0xffffffffu : (((1u << NP) - 1u) << (group_in_warp * NP));
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x / NP) + group_in_block;
+    if (b >= a.B) return;
+    const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
+
+    double *sm_ = smem + (size_t)group_in_block * a.smem_model;
+    double *sL = sm_;   sm_ += NP * LD;   // Cholesky factor, row-major
+    double *sD = sm_;   sm_ += NP * LD;   // P_s[t+1] - P_p[t+1]
+    double *sG = sm_;   sm_ += NP * LD;   // smoothing gain
+    double *sv = sm_;   sm_ += NP;        // broadcast vector
+    double *sa = sm_;   sm_ += NP;        // diag(A)
+    double *sinv = sm_; sm_ += NP;        // 1 / L_ii
+    double *sA = sm_;                     // full A (only when not diagonal)
+
+    const double *Ab = a.A + b * a.A_stride;
+    sa[r] = (r < n) ? Ab[r * n + r] : 0.0;
+    if (!diagA)
+        for (int i = r; i < NP * NP; i += NP) {
+            int rr = i / NP, c = i % NP;
+            sA[rr * LD + c] = (rr < n && c < n) ? Ab[rr * n + c] : 0.0;
+        }
+    __syncwarp(gmask);
+
+    const int64_t T = a.T;
+    const int64_t base = b * T;
+    const bool rv = r < n;
+    int status = 0;
+
+    // t = T-1: smoothed = filtered (kalmanfilter.py:450-451)
+    double xs = rv ? a.fm[(base + T - 1) * n + r] : 0.0;
+    double Ps[NP];
+    {
+        const double *src = a.fc + (base + T - 1) * n * n + r;
+#pragma unroll
+        for (int c = 0; c < NP; ++c) Ps[c] = (rv && c < n) ? src[(int64_t)c * n] : 0.0;
+        if (rv) {
+            a.sm[(base + T - 1) * n + r] = xs;
+            double *dst = a.sc + (base + T - 1) * n * n + r;
+#pragma unroll
+            for (int c = 0; c < NP; ++c)
+                if (c < n) dst[(int64_t)c * n] = Ps[c];
+        }
+    }
+
+    for (int64_t t = T - 2; t >= 0; --t) {
+        // ---- loads ---------------------------------------------------------------------
+        double L[NP];  // starts as row r of P_p[t+1], becomes row r of its Cholesky factor
+        {
+            const double *src = a.pc + (base + t + 1) * n * n + r;
+#pragma unroll
+            for (int c = 0; c < NP; ++c) L[c] = (rv && c < n) ? src[(int64_t)c * n] : ((c == r) ? 1.0 : 0.0);
+        }
+        const double xp = rv ? a.pm[(base + t + 1) * n + r] : 0.0;
+        const double xf = rv ? a.fm[(base + t) * n + r] : 0.0;
+        double Pf[NP];
+        {
+            const double *src = a.fc + (base + t) * n * n + r;
+#pragma unroll
+            for (int c = 0; c < NP; ++c) Pf[c] = (rv && c < n) ? src[(int64_t)c * n] : 0.0;
+        }
+        // D = P_s[t+1] - P_p[t+1] -> shared; delta = x_s[t+1] - x_p[t+1]
+#pragma unroll
+        for (int c = 0; c < NP; c += 2)
+            *reinterpret_cast<double2 *>(sD + r * LD + c) = make_double2(Ps[c] - L[c], Ps[c + 1] - L[c + 1]);
+        const double delta = xs - xp;
+
+        // ---- Cholesky P_p = L L^T (padded rows/cols are the identity) ---------------------
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const double pjj = __shfl_sync(gmask, L[j], j, NP);
+            if (!(pjj > 0.0)) status |= MKF_STATUS_CHOL_FAILED;
+            const double ljj = sqrt(pjj);
+            const double inv = 1.0 / ljj;
+            const double lrj = (r == j) ? ljj : ((r > j) ? L[j] * inv : 0.0);
+            L[j] = lrj;
+            if (r == j) sinv[j] = inv;
+            if (j + 1 < NP) {
+                sv[r] = lrj;
+                __syncwarp(gmask);
+#pragma unroll
+                for (int c = j + 1; c < NP; ++c) L[c] = fma(-lrj, sv[c], L[c]);
+                __syncwarp(gmask);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NP; c += 2)
+            *reinterpret_cast<double2 *>(sL + r * LD + c) =
+                make_double2((c <= r) ? L[c] : 0.0, (c + 1 <= r) ? L[c + 1] : 0.0);
+        sv[r] = delta;
+        __syncwarp(gmask);
+
+        // ---- lane c: solve (L L^T) g = (A P_f)[:, c]  ->  g = row c of G ----------------
+        double z[NP];
+        if (diagA) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) z[i] = sa[i] * Pf[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < NP; ++k) s = fma(sA[i * LD + k], Pf[k], s);
+                z[i] = s;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {  // forward substitution, column oriented
+            z[k] *= sinv[k];
+#pragma unroll
+            for (int i = k + 1; i < NP; ++i) z[i] = fma(-sL[i * LD + k], z[k], z[i]);
+        }
+#pragma unroll
+        for (int k = NP - 1; k >= 0; --k) {  // backward substitution with L^T
+            z[k] *= sinv[k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) z[i] = fma(-sL[k * LD + i], z[k], z[i]);
+        }
+        // rows/cols >= n: P_f row is zero -> z = 0 there.
+
+        // ---- x_s[t] = x_f + G delta -------------------------------------------------------
+        double xnew = xf;
+#pragma unroll
+        for (int i = 0; i < NP; i += 2) {
+            double2 dv = *reinterpret_cast<const double2 *>(sv + i);
+            xnew = fma(z[i], dv.x, xnew);
+            xnew = fma(z[i + 1], dv.y, xnew);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; i += 2)
+            *reinterpret_cast<double2 *>(sG + r * LD + i) = make_double2(z[i], z[i + 1]);
+        __syncwarp(gmask);
+
+        // ---- M = G D (row r), then P_s[t] = P_f + M G^T ---------------------------------
+        double Mrow[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) Mrow[j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+#pragma unroll
+            for (int j = 0; j < NP; j += 2) {
+                double2 dk = *reinterpret_cast<const double2 *>(sD + k * LD + j);
+                Mrow[j] = fma(z[k], dk.x, Mrow[j]);
+                Mrow[j + 1] = fma(z[k], dk.y, Mrow[j + 1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            double s = Pf[j];
+#pragma unroll
+            for (int k = 0; k < NP; k += 2) {
+                double2 gj = *reinterpret_cast<const double2 *>(sG + j * LD + k);
+                s = fma(Mrow[k], gj.x, s);
+                s = fma(Mrow[k + 1], gj.y, s);
+            }
+            Ps[j] = s;
+        }
+        xs = xnew;
+        __syncwarp(gmask);  // shared buffers are rewritten next step
+
+        if (rv) {
+            a.sm[(base + t) * n + r] = xs;
+            double *dst = a.sc + (base + t) * n * n + r;
+#pragma unroll
+            for (int c = 0; c < NP; ++c)
+                if (c < n) dst[(int64_t)c * n] = Ps[c];
+        }
+    }
+    if (r == 0 && a.status) a.status[b] = status;
+}
+
+template <int NP>
+int launch_smoother(SmootherArgs a, cudaStream_t stream) {
+    constexpr int LD = NP + 2;
+    const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
+    int per = 3 * NP * LD + 3 * NP + (diagA ? 0 : NP * LD);
+    per = (per + 1) & ~1;
+    a.smem_model = per;
+    int threads = (NP == 32) ? 64 : 128;
+    size_t smem = (size_t)(threads / NP) * per * sizeof(double);
+    auto kern = smoother_kernel<NP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        mkf_host::set_cuda_error(e);
+        return MKF_ERR_CUDA;
+    }
+    const int mpb = threads / NP;
+    const int64_t blocks = (a.B + mpb - 1) / mpb;
+    kern<<<(unsigned)blocks, threads, smem, stream>>>(a);
+    return mkf_host::check_launch();
+}
+
+// ---- projections ---------------------------------------------------------------------
+// one warp per (model, time step): stage x_t and P_t in shared memory, lane i computes
+// output series i (strided when p > 32).
+__global__ void __launch_bounds__(128) project_kernel(int64_t B, int64_t T, int n, int p,
+                                                      const double *__restrict__ means,
+                                                      const double *__restrict__ covs,
+                                                      const double *__restrict__ Hp, int64_t Hp_stride,
+                                                      double *__restrict__ mout, double *__restrict__ vout) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *sP = smem + (size_t)warp * (n * n + n);
+    double *sx = sP + n * n;
+    const int64_t total = B * T;
+    for (int64_t bt = (int64_t)blockIdx.x * 4 + warp; bt < total; bt += (int64_t)gridDim.x * 4) {
+        const int64_t b = bt / T;
+        __syncwarp();
+        for (int i = lane; i < n * n; i += 32) sP[i] = covs ? covs[bt * n * n + i] : 0.0;
+        for (int i = lane; i < n; i += 32) sx[i] = means[bt * n + i];
+        __syncwarp();
+        const double *Hb = Hp + b * Hp_stride;
+        for (int i = lane; i < p; i += 32) {
+            const double *h = Hb + (int64_t)i * n;
+            double mu = 0.0, var = 0.0;
+            for (int c = 0; c < n; ++c) {
+                const double hc = h[c];
+                mu = fma(hc, sx[c], mu);
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) s = fma(sP[c * n + k], h[k], s);
+                var = fma(hc, s, var);
+            }
+            if (mout) mout[bt * p + i] = mu;
+            if (vout) vout[bt * p + i] = fmax(var, 0.0);  // kalmanfilter.py:601-602
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, const double *fc,
+                            const double *pm, const double *pc, const double *A, int64_t A_stride,
+                            uint32_t flags, double *sm, double *sc, int32_t *status, void *stream) {
+    if (B < 0 || T < 0 || n <= 0) return MKF_ERR_BAD_ARG;
+    if (!fm || !fc || !pm || !pc || !A || !sm || !sc) return MKF_ERR_BAD_ARG;
+    if (n > 32) return MKF_ERR_UNSUPPORTED;
+    if (B == 0 || T == 0) return MKF_OK;
+    SmootherArgs a{};
+    a.B = B; a.T = T; a.n = n; a.fm = fm; a.fc = fc; a.pm = pm; a.pc = pc;
+    a.A = A; a.A_stride = A_stride; a.flags = flags; a.sm = sm; a.sc = sc; a.status = status;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n <= 4) return launch_smoother<4>(a, s);
+    if (n <= 8) return launch_smoother<8>(a, s);
+    if (n <= 16) return launch_smoother<16>(a, s);
+    return launch_smoother<32>(a, s);
+}
+
+extern "C" int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p, const double *means,
+                           const double *covs, const double *Hp, int64_t Hp_stride, double *means_out,
+                           double *var_out, void *stream) {
+    if (B < 0 || T < 0 || n <= 0 || p <= 0 || !means || !Hp) return MKF_ERR_BAD_ARG;
+    if (var_out && !covs) return MKF_ERR_BAD_ARG;
+    if (n > 64) return MKF_ERR_UNSUPPORTED;
+    if (B == 0 || T == 0) return MKF_OK;
+    const int64_t total = B * T;
+    int64_t blocks = (total + 3) / 4;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    size_t smem = 4 * (size_t)(n * n + n) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        mkf_host::set_cuda_error(e);
+        return MKF_ERR_CUDA;
+    }
+    project_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(B, T, n, p, means, covs, Hp, Hp_stride,
+                                                                         means_out, var_out);
+    return mkf_host::check_launch();
+}
