@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- Kalman timesteps*models/s (fp64) of the batched filter -> -2 log L path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+
+One "step" = one pass of the hot path (mkf_dfm_loglik_alpha: parameter map + sequential
+Kalman filter + -2 log L per model, then the deterministic batch reduction and, for
+N > 1, the NCCL all-reduce of the pooled objective) over one batch of synthetic models.
+Default workload ("metric", BASELINE.json `metric`): state_dim 8 (5 series + 3 common
+factors), T = 5000, 32768 independent models per GPU (C4's per-GPU shard size), weak
+scaling.  Under torchrun each rank owns one GPU and its own shard; the time of the K
+steps is the max over ranks.
+
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/, the
+reference itself is pure Python/numba and does not travel to the GPU box) with all host
+threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Kalman timesteps*models/sec (fp64), state_dim=8 T=5000"
+UNIT = "timesteps*models/s"
+
+CONFIGS = {
+    # name: (models per GPU, T, m series, k common factors, missing fraction)
+    "metric": (32768, 5000, 5, 3, 0.0),
+    "c1": (1024, 2000, 5, 3, 0.0),
+    "c4": (32768, 10000, 5, 3, 0.0),
+    "metric_miss50": (32768, 5000, 5, 3, 0.5),
+}
+
+
+def flops_per_step(n, m):
+    """Algorithmic FLOPs of the reference recursion per timestep*model."""
+    return 5 * n * n + m * (5 * n * n + 7 * n + 7)
+
+
+# ------------------------------------------------------------------------------- data
+def make_params(rng, B, m, k):
+    """alpha ~ U(5,50), loadings ~ U(0.3,0.9)/sqrt(k) (SURVEY.md 8d synthetic inputs)."""
+    n = m + k
+    alpha = rng.uniform(5.0, 50.0, (B, n))
+    gamma = rng.uniform(0.3, 0.9, (B, m, k)) / np.sqrt(max(k, 1))
+    return alpha, gamma
+
+
+def simulate_cpu(rng, alpha, gamma, T, miss):
+    B, n = alpha.shape
+    m = gamma.shape[1]
+    phi = np.exp(-1.0 / alpha)
+    comm = np.sum(gamma ** 2, axis=2)
+    q = np.concatenate([(1 - phi[:, :m] ** 2) * (1 - comm), 1 - phi[:, m:] ** 2], axis=1)
+    x = np.zeros((B, n))
+    y = np.empty((B, T, m))
+    sq = np.sqrt(q)
+    for t in range(T):
+        x = phi * x + sq * rng.standard_normal((B, n))
+        y[:, t] = x[:, :m] + np.einsum("bmk,bk->bm", gamma, x[:, m:])
+    if miss > 0:
+        y[rng.random(y.shape) < miss] = np.nan
+    return y
+
+
+def simulate_gpu(torch, dev, seed, alpha, gamma, T, miss):
+    """y simulated from each model on the device (x_t = phi x_{t-1} + sqrt(q) eps, y = H x)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    B, n = alpha.shape
+    m = gamma.shape[1]
+    phi = torch.exp(-1.0 / alpha)
+    comm = (gamma ** 2).sum(dim=2)
+    q = torch.cat([(1 - phi[:, :m] ** 2) * (1 - comm), 1 - phi[:, m:] ** 2], dim=1)
+    sq = torch.sqrt(q)
+    x = torch.zeros(B, n, dtype=torch.float64, device=dev)
+    y = torch.empty(B, T, m, dtype=torch.float64, device=dev)
+    for t in range(T):
+        x = phi * x + sq * torch.randn(B, n, dtype=torch.float64, device=dev, generator=g)
+        y[:, t] = x[:, :m] + torch.einsum("bmk,bk->bm", gamma, x[:, m:])
+    if miss > 0:
+        mask = torch.rand(B, T, m, device=dev, generator=g) < miss
+        y.masked_fill_(mask, float("nan"))
+    return y
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.maxclk = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxclk = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        sm = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": sm, "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(cfg, threads=0, target_models_per_thread=48, seed=99):
+    """Oracle port (oracle/kalman_oracle.c) on the host cores: bounded sample of the workload."""
+    from oracle import kalman_oracle as ko
+
+    ko.build()
+    _, T, m, k, miss = cfg
+    cores = len(os.sched_getaffinity(0))
+    nthreads = threads or cores
+    Bs = max(nthreads * target_models_per_thread, 64)
+    rng = np.random.default_rng(seed)
+    alpha, gamma = make_params(rng, Bs, m, k)
+    Ts = T
+    y = simulate_cpu(rng, alpha, gamma, Ts, miss)
+    n = m + k
+    mats = [ko.dfm_matrices(alpha[b], gamma[b]) for b in range(Bs)]
+    A, Q, H, R = (np.stack([mm[i] for mm in mats]) for i in range(4))
+    ko.filter_loglik_batch(y[: nthreads], A[: nthreads], Q[: nthreads], H[: nthreads], R[: nthreads],
+                           threads=nthreads)  # warm-up (thread pool, page faults)
+
+    def run():
+        t0 = time.perf_counter()
+        mle, _ = ko.filter_loglik_batch(y, A, Q, H, R, threads=nthreads)
+        return time.perf_counter() - t0, mle
+
+    return dict(run=run, Bs=Bs, Ts=Ts, n=n, cores=nthreads,
+                sample="%d models x T=%d (n=%d, m=%d), OpenMP over models, %d threads"
+                       % (Bs, Ts, n, m, nthreads))
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_baseline(cfg)
+    for _ in range(args.warmup):
+        cb["run"]()
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cb["run"]()
+        t += dt
+    value = cb["Bs"] * cb["Ts"] * args.steps / t
+    B, T, m, k, miss = cfg
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": workload_config(args, cfg, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cb["cores"], "kind": "port",
+                         "sample": cb["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, world):
+    B, T, m, k, miss = cfg
+    return {"workload": "%s: %d independent DFM models per GPU, state_dim=%d obs_dim=%d T=%d, "
+                        "filter + -2logL (x0=0, P0=I, warmup=1), missing=%.2f"
+                        % (args.config, B, m + k, m, T, miss),
+            "models_per_gpu": B, "global_models": B * world, "T": T, "state_dim": m + k, "obs_dim": m,
+            "missing_fraction": miss, "parallelism": "dp%d (batch sharded, all-reduce of pooled -2logL)" % world,
+            "l2_policy": "inputs_larger_than_l2 (y = %.2f GB per GPU per step)" % (B * T * m * 8 / 1e9)}
+
+
+# ------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="metric", choices=sorted(CONFIGS))
+    ap.add_argument("--models", type=int, default=0, help="override models per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = list(CONFIGS[args.config])
+    if args.models:
+        cfg[0] = args.models
+    cfg = tuple(cfg)
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from metran_b200.batched import KalmanEngine
+
+    eng = KalmanEngine(device=dev)
+    B, T, m, k, miss = cfg
+    n = m + k
+
+    # ---- synthetic shard of this rank (seeded per rank) ----------------------------------
+    rng = np.random.default_rng(1000 + rank)
+    alpha_h, gamma_h = make_params(rng, B, m, k)
+    alpha = torch.as_tensor(alpha_h, device=dev)
+    gamma = torch.as_tensor(gamma_h, device=dev)
+    y = simulate_gpu(torch, dev, 2000 + rank, alpha, gamma, T, miss)
+    torch.cuda.synchronize()
+
+    out = (eng.empty(B), eng.empty(B, dtype=torch.int64), eng.empty(B, dtype=torch.int32))
+    pooled = eng.empty(1)
+    kern_events = []
+
+    def step(record=False):
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        eng.dfm_loglik_alpha(y, alpha, gamma, out=out)
+        if record:
+            e1.record()
+            kern_events.append((e0, e1))
+        eng.reduce_sum(out[0], out=pooled)
+        if world > 1:
+            dist.all_reduce(pooled)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms_total = t0.elapsed_time(t1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_events]))
+    tt = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, kern_ms = float(tt[0]), float(tt[1])
+    pooled_value = float(pooled[0])
+    bad = int((out[2] != 0).sum())
+
+    # ---- end to end through the public host API: H2D of y + params, D2H of -2logL --------
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+
+        need = B * T * m * 8
+        Be = B
+        while Be > 1024 and need * Be // B > 0.2 * psutil.virtual_memory().available / max(world, 1):
+            Be //= 2
+        y_host = torch.empty(Be, T, m, dtype=torch.float64).pin_memory()
+        y_host.copy_(y[:Be])
+        a_host = torch.as_tensor(alpha_h[:Be]).pin_memory()
+        g_host = torch.as_tensor(gamma_h[:Be]).pin_memory()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            res = eng.dfm_loglik_alpha_host(y_host, a_host, g_host)
+        assert torch.equal(res[0], out[0][:Be].cpu()), "host-streamed path disagrees with resident path"
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            eng.dfm_loglik_alpha_host(y_host, a_host, g_host)
+        torch.cuda.synchronize()
+        wt = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        e2e = {"value": Be * world * T * e2e_steps / float(wt[0]), "unit": UNIT,
+               "h2d_bytes_per_step": int(Be * T * m * 8 + Be * n * 8 + Be * m * k * 8),
+               "d2h_bytes_per_step": int(Be * (8 + 8 + 4)), "models_per_gpu": Be,
+               "api": "KalmanEngine.dfm_loglik_alpha_host (pinned host y, chunked H2D overlapped with the kernel)"}
+        del y_host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (dfm_loglik_kernel<5,3>) -------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = B * T * m * 8 + B * (n + m * k) * 8 + B * 20
+    hbm_ach = alg_bytes / (kern_ms * 1e-3) / 1e9
+    fp64_peak = eng.probe_fp64_tflops()
+    alg_flops = flops_per_step(n, m) * B * T
+    fp64_ach = alg_flops / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tr = json.load(fh)
+        if tr.get("workload") == [B, T, m, k]:
+            traffic = tr.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+        "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+        "kernel": "mkf_dfm::dfm_loglik_kernel<%d,%d>" % (m, k), "kernel_ms": kern_ms,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "limiter": "fp64 FMA pipe (arithmetic intensity %.0f flop/B >> fp64 ridge), see DESIGN.md"
+                   % (alg_flops / alg_bytes),
+        "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
+                 "peak_source": "measured live by mkf_probe_fp64 (DFMA microbenchmark, same process)",
+                 "algorithmic_flops_per_timestep_model": flops_per_step(n, m)},
+    }
+
+    cpu = None
+    if not args.no_cpu:
+        cb = cpu_baseline(cfg)
+        dt, mle_cpu = cb["run"]()
+        cpu = {"value": cb["Bs"] * cb["Ts"] / dt, "unit": UNIT, "cores": cb["cores"], "kind": "port",
+               "sample": cb["sample"], "seconds": dt}
+
+    value = B * world * T * args.steps / (ms_total * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, cfg, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "check": {"pooled_minus2logL": pooled_value, "models_with_status": bad},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -160,6 +160,13 @@ int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p,
 /* Deterministic (fixed-tree) sum of v[0..count) into out[0]; feeds the all-reduce. */
 int mkf_reduce_sum(const double *v, int64_t count, double *out, void *stream);
 
+/*
+ * Measurement aid (no reference counterpart): saturates the fp64 FMA pipe with
+ * blocks x 256 threads x iters x 64 independent DFMAs so bench.py can time the
+ * denominator of the fp64 roofline on the same device and clocks.
+ */
+int mkf_probe_fp64(int32_t blocks, int32_t iters, double *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

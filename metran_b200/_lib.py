@@ -36,6 +36,7 @@ SIGNATURES = {
                      + [_ptr] * 3 + [_ptr]),
     "mkf_project": (ctypes.c_int, [_i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "mkf_reduce_sum": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr]),
+    "mkf_probe_fp64": (ctypes.c_int, [_i32, _i32, _ptr, _ptr]),
 }
 
 _lib = None

@@ -217,6 +217,78 @@ class KalmanEngine:
         _lib.check(self.lib, rc, "mkf_dfm_loglik_alpha")
         return mle, nobs, status
 
+    def dfm_loglik_alpha_host(self, y_host, alpha, gamma, dt=1.0, warmup=1, chunk_models=2048):
+        """Host-resident observations -> -2 log L per model, H2D overlapped with compute.
+
+        ``y_host``: CPU tensor [B,T,m] (pin it for full PCIe speed); ``alpha`` [B,n] and
+        ``gamma`` [B,m,k] | [m,k]: host arrays.  The batch is cut into chunks of
+        ``chunk_models`` models; chunk c+1 is copied on a side stream into the second of
+        two device staging buffers while the filter kernel runs on chunk c.  Returns
+        (mle, nobs, status) as pinned CPU tensors after the final device->host read.
+        """
+        if self.device.type != "cuda":
+            raise _lib.MetranB200Error("dfm_loglik_alpha_host needs a CUDA device")
+        y_host = torch.as_tensor(y_host)
+        B, T, m = (int(s) for s in y_host.shape)
+        chunk = int(min(chunk_models, B))
+        key = (chunk, T, m)
+        st = getattr(self, "_staging", None)
+        if st is None or st["key"] != key:
+            st = dict(key=key, bufs=[self.empty(chunk, T, m), self.empty(chunk, T, m)],
+                      copy_stream=torch.cuda.Stream(self.device),
+                      copied=[torch.cuda.Event(), torch.cuda.Event()],
+                      freed=[torch.cuda.Event(), torch.cuda.Event()])
+            self._staging = st
+        main = torch.cuda.current_stream(self.device)
+        alpha_d = self.tensor(torch.as_tensor(alpha)) if not isinstance(alpha, torch.Tensor) else alpha.to(self.device, non_blocking=True)
+        gamma_d = self.tensor(torch.as_tensor(gamma)) if not isinstance(gamma, torch.Tensor) else gamma.to(self.device, non_blocking=True)
+        mle = self.empty(B)
+        nobs = self.empty(B, dtype=torch.int64)
+        status = self.empty(B, dtype=torch.int32)
+        shared_gamma = gamma_d.dim() == 2
+        for ci, b0 in enumerate(range(0, B, chunk)):
+            b1 = min(B, b0 + chunk)
+            s = ci & 1
+            buf = st["bufs"][s][: b1 - b0]
+            with torch.cuda.stream(st["copy_stream"]):
+                if ci >= 2:
+                    st["copy_stream"].wait_event(st["freed"][s])
+                else:
+                    st["copy_stream"].wait_stream(main)
+                buf.copy_(y_host[b0:b1], non_blocking=True)
+                st["copied"][s].record(st["copy_stream"])
+            main.wait_event(st["copied"][s])
+            self.dfm_loglik_alpha(buf, alpha_d[b0:b1], gamma_d if shared_gamma else gamma_d[b0:b1],
+                                  dt=dt, warmup=warmup, out=(mle[b0:b1], nobs[b0:b1], status[b0:b1]))
+            st["freed"][s].record(main)
+        res = getattr(self, "_host_out", None)
+        if res is None or res[0].shape[0] != B:
+            res = (torch.empty(B, dtype=torch.float64).pin_memory(),
+                   torch.empty(B, dtype=torch.int64).pin_memory(),
+                   torch.empty(B, dtype=torch.int32).pin_memory())
+            self._host_out = res
+        res[0].copy_(mle, non_blocking=True)
+        res[1].copy_(nobs, non_blocking=True)
+        res[2].copy_(status, non_blocking=True)
+        main.synchronize()
+        return res
+
+    def probe_fp64_tflops(self, blocks=148 * 8, iters=4096, reps=5):
+        """Measured fp64 FMA throughput (TFLOP/s) of this device: roofline denominator."""
+        scratch = self.empty(1)
+        best = None
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = self.lib.mkf_probe_fp64(int(blocks), int(iters), _ptr(scratch), self._stream())
+            e1.record()
+            _lib.check(self.lib, rc, "mkf_probe_fp64")
+            torch.cuda.synchronize(self.device)
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        flops = blocks * 256.0 * iters * 64 * 2
+        return flops / (best * 1e-3) / 1e12
+
     def reduce_sum(self, v, out=None):
         """Deterministic sum of a device vector into a 1-element tensor (all-reduce input)."""
         v = self.tensor(v)

@@ -59,3 +59,29 @@ extern "C" int mkf_reduce_sum(const double *v, int64_t count, double *out, void 
     reduce_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v, count, out);
     return mkf_host::check_launch();
 }
+
+namespace {
+// fp64 FMA pipe probe for the bench's roofline denominator: 8 independent DFMA chains per
+// thread, `iters` rounds; result written so the compiler keeps the chain.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double *__restrict__ out) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) out[0] = s;
+}
+}  // namespace
+
+// Launches blocks x 256 threads, each doing iters*64 DFMAs (= iters*128 flops per thread).
+extern "C" int mkf_probe_fp64(int32_t blocks, int32_t iters, double *scratch, void *stream) {
+    if (blocks <= 0 || iters <= 0 || !scratch) return MKF_ERR_BAD_ARG;
+    fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, scratch);
+    return mkf_host::check_launch();
+}

@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference's Kalman object, backed by the CUDA library.
+
+``SPKalmanFilter`` keeps the public surface of the reference class
+(metran/kalmanfilter.py:479-778: same method names, arguments, result attributes and
+error behaviour) so that ``Metran`` -- which only ever touches the attributes listed in
+SURVEY.md section 8b -- runs unmodified on top of it (see install.py).  The two module
+functions are the reference's plug-in points:
+
+* ``seqkalmanfilter_cuda``  : the 9-in / 7-out ``filtermethod`` (kalmanfilter.py:236-400)
+* ``kalmansmoother_cuda``   : ``kalmansmoother`` (kalmanfilter.py:403-476)
+
+All arithmetic happens in libmetran_b200.so; this file only packs arguments.  There is
+no CPU engine here: the product fails loudly without the CUDA library / a CUDA device.
+"""
+from logging import getLogger
+
+import numpy as np
+
+from . import _lib
+
+logger = getLogger(__name__)
+
+_ENGINE_NAMES = ("cuda", "numba", "numpy")
+_engine_singleton = None
+
+
+def _engine(engine=None):
+    global _engine_singleton
+    if engine is not None:
+        return engine
+    if _engine_singleton is None:
+        from .batched import KalmanEngine
+
+        _engine_singleton = KalmanEngine()
+    return _engine_singleton
+
+
+def set_default_engine(engine):
+    """Install a KalmanEngine used by every SPKalmanFilter created afterwards."""
+    global _engine_singleton
+    _engine_singleton = engine
+
+
+def pack_observations(values):
+    """NaN-coded [T,m] array -> (observations, observation_indices, observation_count).
+
+    Vectorised restatement of SPKalmanFilter.set_observations (kalmanfilter.py:646-674):
+    a slot is observed when finite and ``value + 1e10 != 0`` (:657, :666-667);
+    ``observation_indices`` is float64, ascending, zero padded (:659, :674);
+    ``observations`` carries 0.0 at missing slots (:661, :673).
+    """
+    y = np.asarray(values, dtype=np.float64)
+    finite = np.isfinite(y)
+    observed = finite & ((np.where(finite, y, 0.0) + 1e10) != 0.0)
+    observations = np.where(observed, y, 0.0)
+    count = observed.sum(axis=1).astype(np.int64)
+    T, m = y.shape
+    # stable argsort puts observed columns first, in ascending column order
+    order = np.argsort(~observed, axis=1, kind="stable")
+    keep = np.arange(m)[None, :] < count[:, None]
+    indices = np.where(keep, order, 0).astype(np.float64)
+    return observations, indices, count, observed
+
+
+def unpack_observations(observations, observation_indices, observation_count):
+    """Inverse of pack_observations: back to the NaN-coded matrix the kernels consume.
+
+    The kernels process the observed series of a time step in ascending index order (the
+    order set_observations produces); any other order is rejected rather than silently
+    reordered.
+    """
+    obs = np.asarray(observations, dtype=np.float64)
+    idx = np.asarray(observation_indices)
+    cnt = np.asarray(observation_count).astype(np.int64)
+    T, m = obs.shape
+    if idx.shape != (T, m) or cnt.shape != (T,):
+        raise ValueError("observation_indices / observation_count do not match observations")
+    if cnt.min(initial=0) < 0 or cnt.max(initial=0) > m:
+        raise ValueError("observation_count out of range")
+    cols = np.arange(m)[None, :]
+    valid = cols < cnt[:, None]
+    ii = idx.astype(np.int64)
+    if np.any(valid & ((ii < 0) | (ii >= m))):
+        raise ValueError("observation_indices out of range")
+    asc = (ii[:, 1:] > ii[:, :-1]) | ~valid[:, 1:]
+    if not np.all(asc):
+        raise ValueError("observation_indices must be strictly ascending within a time step "
+                         "(the order SPKalmanFilter.set_observations produces)")
+    observed = np.zeros((T, m), dtype=bool)
+    rows = np.broadcast_to(np.arange(T)[:, None], (T, m))
+    observed[rows[valid], ii[valid]] = True
+    y = np.where(observed, obs, np.nan)
+    if np.any(observed & ~(np.isfinite(obs) & (obs + 1e10 != 0.0))):
+        raise ValueError("an indexed observation is not finite")
+    return y
+
+
+def _structure_flags(A, Q):
+    A = np.asarray(A)
+    Q = np.asarray(Q)
+    f = 0
+    if np.count_nonzero(A - np.diag(np.diag(A))) == 0:
+        f |= _lib.FLAG_A_DIAGONAL
+    if np.count_nonzero(Q - np.diag(np.diag(Q))) == 0:
+        f |= _lib.FLAG_Q_DIAGONAL
+    return f
+
+
+def _filter_device(engine, y_dev, A, Q, H, R, x0, P0, covariances=True):
+    A, Q, H, R = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, Q, H, R))
+    n = A.shape[0]
+    if A.shape != (n, n) or Q.shape != (n, n) or H.shape[1] != n or R.shape != (H.shape[0],):
+        raise ValueError("inconsistent state-space matrices")
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    P0 = np.ascontiguousarray(P0, dtype=np.float64)
+    return engine.filter_history(y_dev, A, Q, H, R, x0=x0[None], P0=P0[None],
+                                 flags=_structure_flags(A, Q), covariances=covariances)
+
+
+def _history_to_numpy(out):
+    cnt = out["cnt"][0].cpu().numpy()
+    seen = cnt > 0
+    sig = out["sigma"][0].cpu().numpy()
+    det = out["detf"][0].cpu().numpy()
+    sigmacount = int(seen.sum())
+    T = cnt.shape[0]
+    # reference contract: arrays of length T whose first `sigmacount` entries are valid
+    sigmas = np.zeros(T)
+    detfs = np.zeros(T)
+    sigmas[:sigmacount] = sig[seen]
+    detfs[:sigmacount] = det[seen]
+    return (sigmas, detfs, sigmacount,
+            out["fm"][0].cpu().numpy(), out["fc"][0].cpu().numpy(),
+            out["pm"][0].cpu().numpy(), out["pc"][0].cpu().numpy())
+
+
+def seqkalmanfilter_cuda(observations, transition_matrix, transition_covariance, observation_matrix,
+                         observation_variance, observation_indices, observation_count,
+                         filtered_state_mean, filtered_state_covariance, engine=None):
+    """CUDA ``filtermethod``: same 9 inputs / 7 outputs as seqkalmanfilter
+    (metran/kalmanfilter.py:243-253, 392-400).  Runs mkf_filter_history with B = 1."""
+    eng = _engine(engine)
+    y = unpack_observations(observations, observation_indices, observation_count)
+    out = _filter_device(eng, eng.tensor(y[None]), transition_matrix, transition_covariance,
+                         observation_matrix, observation_variance,
+                         filtered_state_mean, filtered_state_covariance)
+    return _history_to_numpy(out)
+
+
+def kalmansmoother_cuda(filtered_state_means, filtered_state_covariances, predicted_state_means,
+                        predicted_state_covariances, transition_matrix, engine=None):
+    """CUDA ``kalmansmoother`` (metran/kalmanfilter.py:403-476): returns (means, covariances)."""
+    eng = _engine(engine)
+    A = np.ascontiguousarray(transition_matrix, dtype=np.float64)
+    flags = _lib.FLAG_A_DIAGONAL if np.count_nonzero(A - np.diag(np.diag(A))) == 0 else 0
+    sm, sc, status = eng.smoother(np.asarray(filtered_state_means)[None], np.asarray(filtered_state_covariances)[None],
+                                  np.asarray(predicted_state_means)[None], np.asarray(predicted_state_covariances)[None],
+                                  A, flags=flags)
+    if int(status[0]) & _lib.STATUS_CHOL_FAILED:
+        logger.warning("Kalman smoother: a predicted covariance is not positive definite.")
+    return sm[0].cpu().numpy(), sc[0].cpu().numpy()
+
+
+class SPKalmanFilter:
+    """Kalman filter class for Metran, CUDA engine (mirror of kalmanfilter.py:479-778).
+
+    Parameters
+    ----------
+    engine : str, optional
+        "cuda" (default).  "numba" / "numpy" are accepted for call compatibility with
+        ``Metran.solve(engine=...)`` (metran.py:991, 1025) and run the same CUDA kernels;
+        this package has no CPU engine.
+    """
+
+    def __init__(self, engine="cuda", device_engine=None):
+        self.init_states()
+        self.detfs = None
+        self.sigmas = None
+        self.nobs = None
+        self.mask = False
+        self.engine = engine
+        self._eng = device_engine
+        self._y_dev = None
+        self._hist = None
+        self.filtermethod = self._filtermethod
+
+    # ---------------------------------------------------------------- reference surface
+    def init_states(self):
+        """Reset state means and covariances (kalmanfilter.py:506-518)."""
+        self.filtered_state_means = None
+        self.filtered_state_covariances = None
+        self.predicted_state_means = None
+        self.predicted_state_covariances = None
+        self.smoothed_state_means = None
+        self.smoothed_state_covariances = None
+        self._hist = None
+
+    def set_matrices(self, transition_matrix, transition_covariance, observation_matrix, observation_variance):
+        """Set the state-space matrices (kalmanfilter.py:520-548)."""
+        self.transition_matrix = transition_matrix
+        self.transition_covariance = transition_covariance
+        self.observation_matrix = observation_matrix
+        self.observation_variance = observation_variance
+        self.nstate = np.int64(self.transition_matrix.shape[0])
+
+    def get_mle(self, warmup=1):
+        """-2 log L from the stored sigmas/detfs (kalmanfilter.py:550-567, quirk Q4)."""
+        detfs = self.detfs[warmup:]
+        sigmas = self.sigmas[warmup:]
+        nobs = np.sum(self.observation_count[warmup:])
+        return nobs * np.log(2 * np.pi) + np.sum(detfs) + np.sum(sigmas)
+
+    def set_observations(self, oseries):
+        """Pack observations (kalmanfilter.py:646-674) and upload them once.
+
+        ``oseries``: pandas.DataFrame (or 2-D array), NaN = missing.  Besides the
+        reference's three host arrays the NaN-coded matrix is kept resident on the device,
+        so objective evaluations and mask toggles do not re-upload it.
+        """
+        self.oseries_index = getattr(oseries, "index", None)
+        values = np.asarray(oseries, dtype=np.float64)
+        if values.ndim != 2:
+            raise ValueError("oseries must be two-dimensional")
+        (self.observations, self.observation_indices, self.observation_count,
+         observed) = pack_observations(values)
+        y = np.where(observed, values, np.nan)
+        eng = self._device_engine()
+        self._y_dev = eng.tensor(y[None])
+        self._hist = None
+
+    def run_filter(self, initial_state_mean=None, initial_state_covariance=None, engine=None):
+        """Run the Kalman filter (kalmanfilter.py:696-778) on the device."""
+        if self.mask:
+            logger.info("Running Kalman filter with masked observations.")
+        if engine is not None:
+            if engine not in _ENGINE_NAMES:
+                msg = "Unknown engine defined in run_filter."
+                logger.error(msg)
+                raise Exception(msg)
+            self.engine = engine
+        if initial_state_mean is None:
+            initial_state_mean = np.zeros(self.nstate)
+        if initial_state_covariance is None:
+            initial_state_covariance = np.eye(self.nstate)
+
+        (sigmas, detfs, sigmacount, filtered_state_means, filtered_state_covariances,
+         predicted_state_means, predicted_state_covariances) = self.filtermethod(
+            self.observations, self.transition_matrix, self.transition_covariance,
+            self.observation_matrix, self.observation_variance, self.observation_indices,
+            self.observation_count, initial_state_mean, initial_state_covariance)
+
+        self.sigmas = sigmas[:sigmacount]
+        self.detfs = detfs[:sigmacount]
+        self.filtered_state_means = filtered_state_means
+        self.filtered_state_covariances = filtered_state_covariances
+        self.predicted_state_means = predicted_state_means
+        self.predicted_state_covariances = predicted_state_covariances
+
+    def run_smoother(self):
+        """Filter, then RTS smoother (kalmanfilter.py:676-694); history stays on the device
+        between the two kernels."""
+        self.run_filter()
+        eng = self._device_engine()
+        h = self._hist
+        A = np.ascontiguousarray(self.transition_matrix, dtype=np.float64)
+        flags = h["flags"] & _lib.FLAG_A_DIAGONAL
+        sm, sc, status = eng.smoother(h["fm"], h["fc"], h["pm"], h["pc"], A, flags=flags)
+        if int(status[0]) & _lib.STATUS_CHOL_FAILED:
+            logger.warning("Kalman smoother: a predicted covariance is not positive definite.")
+        self._hist["sm"], self._hist["sc"] = sm, sc
+        self.smoothed_state_means = sm[0].cpu().numpy()
+        self.smoothed_state_covariances = sc[0].cpu().numpy()
+
+    def simulate(self, observation_matrix, method="smoother"):
+        """Projected means and variances (kalmanfilter.py:569-603), one kernel for all t."""
+        means, covs = self._moments(method)
+        eng = self._device_engine()
+        mu, var = eng.project(means, covs, np.ascontiguousarray(observation_matrix, dtype=np.float64))
+        return list(mu[0].cpu().numpy()), list(var[0].cpu().numpy())
+
+    def decompose(self, observation_matrix, method="smoother"):
+        """Specific / common dynamic factor contributions (kalmanfilter.py:605-644)."""
+        if method == "filter":
+            means = self.filtered_state_means
+        else:
+            means = self.smoothed_state_means
+        Hs = np.asarray(observation_matrix, dtype=np.float64)
+        nsdf = self.observation_matrix.shape[0]
+        ncdf = self.observation_matrix.shape[1] - nsdf
+        eng = self._device_engine()
+        # sdf: project with the specific block only; cdf k: rank-one outer products
+        Hsdf = np.zeros_like(Hs)
+        Hsdf[:, :nsdf] = Hs[:, :nsdf]
+        sdf, _ = eng.project(means[None], None, Hsdf, variances=False)
+        sdf_means = list(sdf[0].cpu().numpy())
+        cdf_means = []
+        for k in range(ncdf):
+            Hk = np.zeros_like(Hs)
+            Hk[:, nsdf + k] = Hs[:, nsdf + k]
+            ck, _ = eng.project(means[None], None, Hk, variances=False)
+            cdf_means.append(list(ck[0].cpu().numpy()))
+        return (sdf_means, cdf_means)
+
+    # ---------------------------------------------------------------------- internals
+    def _device_engine(self):
+        if self._eng is None:
+            self._eng = _engine()
+        return self._eng
+
+    def _moments(self, method):
+        h = self._hist
+        if method == "filter":
+            if h is not None:
+                return h["fm"], h["fc"]
+            return self.filtered_state_means[None], self.filtered_state_covariances[None]
+        if h is not None and "sm" in h:
+            return h["sm"], h["sc"]
+        return self.smoothed_state_means[None], self.smoothed_state_covariances[None]
+
+    def _filtermethod(self, observations, A, Q, H, R, observation_indices, observation_count, x0, P0):
+        """Bound CUDA filtermethod: uses the device-resident observations when the host
+        arrays are the ones set_observations produced."""
+        eng = self._device_engine()
+        if (self._y_dev is not None and observations is self.observations
+                and observation_indices is self.observation_indices
+                and observation_count is self.observation_count):
+            y_dev = self._y_dev
+        else:
+            y_dev = eng.tensor(unpack_observations(observations, observation_indices, observation_count)[None])
+        out = _filter_device(eng, y_dev, A, Q, H, R, x0, P0)
+        self._hist = out
+        return _history_to_numpy(out)

@@ -1,0 +1,207 @@
+"""CPU-only tests: the C ABI surface, the host-side packing logic and the mirrors of the
+reference's Kalman object / objective, driven through tests/fakelib.py (oracle-backed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from conftest import CASE_TAGS, ROOT
+
+from fakelib import FakeLib
+from oracle import kalman_oracle as ko
+
+
+@pytest.fixture()
+def eng():
+    from metran_b200.batched import KalmanEngine
+
+    return KalmanEngine(lib=FakeLib(), device="cpu")
+
+
+# ------------------------------------------------------------------------------- ABI
+def test_library_exports_every_declared_symbol():
+    from metran_b200 import _lib, build
+
+    header = open(os.path.join(ROOT, "include", "metran_b200.h")).read()
+    declared = set(re.findall(r"\b(mkf_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    path = build.build()
+    L = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(L, name), "libmetran_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.load().mkf_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    from metran_b200 import _lib
+    from metran_b200.batched import KalmanEngine
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MetranB200Error):
+        KalmanEngine()
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the checker (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "metran_b200")
+    pat = re.compile(r"^\s*(from|import)\s+(oracle|tests|fakelib)\b", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), "%s imports test infrastructure" % f
+                assert "kalman_oracle" not in src, f
+
+
+# --------------------------------------------------------------------------- packing
+@pytest.mark.parametrize("tag", CASE_TAGS)
+def test_pack_unpack_observations(cases, tag):
+    from metran_b200.kalmanfilter import pack_observations, unpack_observations
+
+    c = cases[tag]
+    obs, idx, cnt, observed = pack_observations(c["y"])
+    assert np.array_equal(obs, c["obs"]) and np.array_equal(idx, c["oidx"]) and np.array_equal(cnt, c["ocnt"])
+    y = unpack_observations(obs, idx, cnt)
+    assert np.array_equal(np.isnan(y), ~observed)
+    assert np.array_equal(y[observed], c["y"][observed])
+
+
+def test_unpack_rejects_descending_indices():
+    from metran_b200.kalmanfilter import unpack_observations
+
+    obs = np.ones((2, 3))
+    idx = np.array([[2.0, 0.0, 0.0], [0.0, 1.0, 2.0]])
+    with pytest.raises(ValueError):
+        unpack_observations(obs, idx, np.array([2, 3]))
+
+
+# ------------------------------------------------------------------- Kalman object
+def test_filtermethod_contract(eng, cases):
+    from metran_b200.kalmanfilter import kalmansmoother_cuda, seqkalmanfilter_cuda
+
+    c = cases["dfm_n8_m5_miss30"]
+    res = seqkalmanfilter_cuda(c["obs"], c["A"], c["Q"], c["H"], c["R"], c["oidx"], c["ocnt"],
+                               c["x0"], c["P0"], engine=eng)
+    sig, det, ns, fm, fc, pm, pc = res
+    assert ns == c["sigmas"].shape[0] and sig.shape[0] >= ns
+    np.testing.assert_allclose(sig[:ns], c["sigmas"], atol=1e-12)
+    np.testing.assert_allclose(det[:ns], c["detfs"], atol=1e-12)
+    for got, key in ((fm, "fm"), (fc, "fc"), (pm, "pm"), (pc, "pc")):
+        np.testing.assert_allclose(got, c[key], atol=1e-12)
+    sm, sc = kalmansmoother_cuda(fm, fc, pm, pc, c["A"], engine=eng)
+    np.testing.assert_allclose(sm, c["sm"], atol=1e-12)
+    np.testing.assert_allclose(sc, c["sc"], atol=1e-12)
+
+
+def test_spkalmanfilter_mirror_on_b21(eng, b21):
+    from metran_b200.kalmanfilter import SPKalmanFilter
+
+    g = b21
+    kf = SPKalmanFilter(device_engine=eng)
+    kf.set_observations(g["y"])
+    assert np.array_equal(kf.observation_count, g["observation_count"])
+    kf.set_matrices(g["A_opt"], g["Q_opt"], g["H_opt"], g["R_opt"])
+    assert kf.nstate == 6
+    kf.run_filter()
+    np.testing.assert_allclose(kf.sigmas, g["sigmas"], atol=1e-12)
+    np.testing.assert_allclose(kf.detfs, g["detfs"], atol=1e-12)
+    assert abs(kf.get_mle() - float(g["mle_opt"])) < 1e-9
+    kf.run_smoother()
+    sel = g["sel"]
+    np.testing.assert_allclose(kf.smoothed_state_means, g["sm_full"], atol=1e-11)
+    np.testing.assert_allclose(kf.smoothed_state_covariances[sel], g["sc"], atol=1e-11)
+    Hs = g["H_opt"] * g["oseries_std"][:, None]
+    means, var = kf.simulate(Hs)
+    assert isinstance(means, list) and len(means) == g["y"].shape[0]
+    np.testing.assert_allclose(np.asarray(means)[sel] + g["oseries_mean"], g["sim_means"], atol=1e-10)
+    np.testing.assert_allclose(np.asarray(var)[sel], g["sim_variances"], atol=1e-10)
+    means_f, _ = kf.simulate(Hs, method="filter")
+    np.testing.assert_allclose(np.asarray(means_f)[sel] + g["oseries_mean"], g["sim_means_filter"], atol=1e-10)
+    sdf, cdf = kf.decompose(Hs)
+    np.testing.assert_allclose(np.asarray(sdf)[sel, 0] + g["oseries_mean"][0], g["decompose_first"][:, 0], atol=1e-10)
+    np.testing.assert_allclose(np.asarray(cdf[0])[sel, 0], g["decompose_first"][:, 1], atol=1e-10)
+
+
+def test_engine_error_behaviour(eng, b21):
+    from metran_b200.kalmanfilter import SPKalmanFilter
+
+    kf = SPKalmanFilter(engine="numba", device_engine=eng)   # accepted, runs the CUDA path
+    kf.set_observations(b21["y"][:50])
+    kf.set_matrices(b21["A_opt"], b21["Q_opt"], b21["H_opt"], b21["R_opt"])
+    with pytest.raises(Exception, match="Unknown engine defined in run_filter."):
+        kf.run_filter(engine="fortran")
+    kf.run_filter(engine="cuda")
+    assert kf.filtered_state_means.shape == (50, 6)
+
+
+# ---------------------------------------------------------------- Metran-facing mirror
+def test_dfm_objective_and_batch(eng, b21):
+    from metran_b200.dfm import DynamicFactorModel
+
+    g = b21
+    mdl = DynamicFactorModel(g["y"], g["factors"], engine=eng)
+    assert abs(mdl.get_mle(g["alpha_init"]) - 2384.792799342231) < 1e-9
+    assert abs(mdl.objfunction(g["alpha_opt"]) - float(g["mle_opt"])) < 1e-9
+    got = mdl.get_mle_batch(g["alpha_draws"])
+    np.testing.assert_allclose(got, g["mle_draws"], rtol=1e-12, atol=1e-9)
+    A, Q, H, R = mdl._get_matrices(g["alpha_opt"])
+    for a, key in ((A, "A_opt"), (Q, "Q_opt"), (H, "H_opt"), (R, "R_opt")):
+        assert np.array_equal(a, g[key])
+    if hasattr(eng.lib, "calls"):
+        assert eng.lib.calls[-1][0] == "mkf_dfm_loglik_alpha" and eng.lib.calls[-1][1] == 16
+
+
+def test_dfm_solve_reaches_reference_optimum(eng, nbmodel):
+    """L-BFGS-B with all finite-difference points of a gradient in one batched call."""
+    from metran_b200.dfm import DynamicFactorModel
+
+    g = nbmodel
+    mdl = DynamicFactorModel(g["y"], g["factors"], engine=eng)
+    ok, x, stderr = mdl.solve()
+    assert ok
+    assert abs(mdl.parameters["obj_func"] - float(g["obj_opt"])) < 1e-5
+    np.testing.assert_allclose(x, g["alpha_opt"], rtol=2e-3)
+    assert mdl.parameters["batched_launches"] >= 1
+    # every batched call carried nparam finite-difference points
+    if hasattr(eng.lib, "calls"):
+        fd = [c for c in eng.lib.calls if c[0] == "mkf_dfm_loglik_alpha" and c[1] == mdl.nstate]
+        assert len(fd) == mdl.parameters["batched_launches"]
+
+
+def test_dfm_mask_unmask(eng, b21):
+    from metran_b200.dfm import DynamicFactorModel
+
+    g = b21
+    mdl = DynamicFactorModel(g["y"], g["factors"], engine=eng)
+    Hs = g["H_opt"] * g["oseries_std"][:, None]
+    # quirk Q7: the reference's masked getter reuses the matrices of the LAST objective call
+    p = g["alpha_opt"]
+    mask = np.zeros_like(g["y"], dtype=bool)
+    row, col = int(g["mask_row"]), int(g["mask_col"])
+    mask[row, col] = True
+    before = mdl.get_simulated_means(p, Hs)[row, col]
+    mdl.mask_observations(mask)
+    after = mdl.get_simulated_means(p, Hs)
+    var = mdl.get_simulated_variances(p, Hs)
+    mdl.unmask_observations()
+    assert before != after[row, col]
+    want = g["masked_sim_row"]            # [mean, lower, upper] of the 95 % interval
+    assert abs(after[row, col] + g["oseries_mean"][col] - want[0]) < 1e-6
+    half = 1.959963984540054 * np.sqrt(var[row, col])
+    assert abs((want[2] - want[1]) / 2 - half) < 1e-6
+
+
+# ------------------------------------------------------------------------ sharding
+def test_shard_bounds_cover_batch():
+    from metran_b200.distributed import shard_bounds
+
+    for total in (0, 1, 7, 64, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
