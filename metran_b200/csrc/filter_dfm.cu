@@ -2,6 +2,46 @@
 #include "filter_dfm.cuh"
 
 namespace mkf_dfm {
+
+// cuTensorMapEncodeTiled is a driver-API entry point; it is resolved through the runtime
+// (cudaGetDriverEntryPoint) so the library does not link libcuda directly.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
+                      int box_rows, int box_elems) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return MKF_ERR_UNSUPPORTED;
+    if (row_elems <= 0 || rows <= 0 || row_elems >= (1LL << 32) || rows >= (1LL << 32)) return MKF_ERR_UNSUPPORTED;
+    if ((row_stride * 8) % 16 != 0 || row_stride * 8 >= (1LL << 40) || row_stride < row_elems) return MKF_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride * 8};  // bytes between model rows
+    cuuint32_t box[2] = {(cuuint32_t)box_elems, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(y), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+    return r == CUDA_SUCCESS ? MKF_OK : MKF_ERR_UNSUPPORTED;
+}
+
 template <> int launch_for_m<0>(int, const DfmArgs &, cudaStream_t);
 template <> int launch_for_m<1>(int, const DfmArgs &, cudaStream_t);
 template <> int launch_for_m<2>(int, const DfmArgs &, cudaStream_t);
@@ -12,8 +52,8 @@ static int run(int m, int k, DfmArgs &a, cudaStream_t s) {
     if (!a.y || !a.mle || (k > 0 && !a.gamma)) return MKF_ERR_BAD_ARG;
     if (m > kMaxM || k > kMaxK) return MKF_ERR_UNSUPPORTED;
     if (a.B == 0) return MKF_OK;
-    // bulk (TMA) staging needs every model row 16-byte aligned
-    a.use_bulk = ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && ((a.y_stride & 1) == 0);
+    // TMA staging needs every model row 16-byte aligned (else: cp.async staging)
+    a.use_tma = ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && ((a.y_stride & 1) == 0);
     switch (k) {
         case 0: return launch_for_m<0>(m, a, s);
         case 1: return launch_for_m<1>(m, a, s);

@@ -10,15 +10,21 @@
 //   d = P h      costs N*K FMAs instead of N^2
 //   f = h.d      costs K FMAs
 // and P stays symmetric, so only its upper triangle (N(N+1)/2 doubles) lives in registers.
-// One thread owns one model for all T steps: no shuffles, no shared-memory traffic for
-// the state; the fp64 pipe is the bound (kernel K1).
+// One thread owns one model for all T steps: no shuffles and no shared-memory traffic for
+// the state; the fp64 FMA pipe is the bound (kernel K1).
 //
 // Observations y[B][T][M] (model-major, NaN = missing) are streamed by the TMA engine:
-// every lane issues one cp.async.bulk per time tile for its own model row into a
-// shared-memory ring (mbarrier complete_tx), and reads it back with LDS.  The row pitch
-// is padded to 2 (mod 4) doubles so the 64-bit reads of a warp are 2-way bank conflicted
-// at worst.  If the rows are not 16-byte aligned the kernel stages with 8-byte cp.async.
+// one elected lane issues ONE cp.async.bulk.tensor.2d per time tile -- a box of 32 model
+// rows x (TT*M) contiguous doubles described by a CUtensorMap over y viewed as [B][T*M] --
+// into a two-stage shared-memory ring (mbarrier complete_tx); lanes read their own row
+// back with LDS.  When the rows are not 16-byte aligned (odd T*M) the kernel stages with
+// 8-byte cp.async instead.  phi stays in registers (80 uses per step); q and Gamma are
+// read from shared memory ([index][lane]) so that the register file is left to P, x and
+// the instruction scheduler.
 #pragma once
+#include <cuda.h>
+#include <string.h>
+
 #include "mkf_common.cuh"
 
 namespace mkf_dfm {
@@ -33,22 +39,40 @@ struct DfmArgs {
     int64_t phi_stride, q_stride, gamma_stride, r_stride, alpha_stride;
     double dt;
     int warmup;
-    int use_bulk;  // rows 16-byte aligned -> cp.async.bulk staging
+    int use_tma;  // rows 16-byte aligned -> 2-D tensor-map staging
     double *mle;
     int64_t *nobs;
     int32_t *status;
 };
 
-constexpr int kBlock = 64;   // threads per CTA (2 independent warps)
-constexpr int kTT = 8;       // time steps per tile
+constexpr int kBlock = 32;  // one warp per CTA: CTAs spread evenly over the 592 SMSPs
 constexpr int kStages = 2;
 
-__host__ __device__ constexpr int tile_pitch(int M) {
-    int p = (kTT * M + 1) & ~1;       // even -> rows stay 16-byte aligned
-    return (p % 4 == 0) ? p + 2 : p;  // p = 2 (mod 4): at most 2-way LDS.64 conflicts
+// time steps per tile: TT*M even (16-byte rows) and, where possible, TT*M = 2 (mod 4) so the
+// 64-bit LDS of a warp (row pitch TT*M doubles) is only 2-way bank conflicted
+__host__ __device__ constexpr int tile_steps(int M) {
+    return (M % 2 == 1) ? 6 : ((M % 4 == 2) ? 5 : 6);
 }
-__host__ __device__ constexpr size_t smem_bytes(int M) {
-    return (size_t)(kBlock / 32) * (kStages * 32 * tile_pitch(M) * sizeof(double) + kStages * sizeof(uint64_t));
+__host__ __device__ constexpr int const_count(int M, int K) { return (M + K) + M * K; }
+__host__ __device__ constexpr int warp_doubles(int M, int K) {
+    return kStages * 32 * tile_steps(M) * M + 32 * const_count(M, K);
+}
+__host__ __device__ constexpr size_t smem_bytes(int M, int K) {
+    return 128 + (size_t)(kBlock / 32) * (warp_doubles(M, K) * sizeof(double) + kStages * sizeof(uint64_t));
+}
+
+__device__ __forceinline__ double lds_f64(const double *p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
 }
 
 // index of (r, c), r <= c, in the packed upper triangle of an N x N matrix
@@ -61,26 +85,31 @@ __host__ __device__ constexpr int sym(int r, int c) {
     return r <= c ? tri<N>(r, c) : tri<N>(c, r);
 }
 
-template <int M, int K>
-__global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a) {
+template <int M, int K, bool HASR>
+__global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, const __grid_constant__ CUtensorMap ymap) {
     constexpr int N = M + K;
     constexpr int NT = N * (N + 1) / 2;
-    constexpr int PITCH = tile_pitch(M);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TT = tile_steps(M);
+    constexpr int PITCH = TT * M;  // doubles per model row of a tile
+    constexpr int WARP_DOUBLES = warp_doubles(M, K);
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem_al =
+        smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // TMA destinations: 128 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * kStages * 32 * PITCH;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) +
-                                                  (size_t)(kBlock / 32) * kStages * 32 * PITCH) +
-                     warp * kStages;
-    const int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    double *ring = reinterpret_cast<double *>(smem_al) + (size_t)warp * WARP_DOUBLES;
+    double *cst = ring + kStages * 32 * PITCH + lane;  // constant i of this lane: cst[i * 32]
+    uint64_t *bars =
+        reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_al) + (size_t)(kBlock / 32) * WARP_DOUBLES) +
+        warp * kStages;
+    const int64_t b0 = (int64_t)blockIdx.x * kBlock + (threadIdx.x & ~31);  // first model of the warp
+    const int64_t b = b0 + lane;
     const bool active = b < a.B;
-    const unsigned act_mask = __ballot_sync(0xffffffffu, active);
-    if (act_mask == 0) return;
-    const int nactive = __popc(act_mask);
-    const bool bulk = a.use_bulk != 0;
+    if (b0 >= a.B) return;
+    const bool tma = a.use_tma != 0;
+    const bool shared_y = a.y_stride == 0;
 
-    if (bulk) {
+    if (tma) {
         if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
@@ -90,14 +119,16 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a) {
     }
 
     // ---- per-model constants ---------------------------------------------------------
-    double phi[N], q[N], G[M * K + 1], R[M];
-    const int64_t bb = active ? b : 0;
+    double phi[N];
+    double R[M];
+    const int64_t bb = active ? b : b0;  // idle lanes of a ragged last warp shadow its first model
     {
+        double q[N], G[M * K + 1];
         const double *gp = a.gamma + bb * a.gamma_stride;
 #pragma unroll
         for (int i = 0; i < M * K; ++i) G[i] = gp[i];
 #pragma unroll
-        for (int i = 0; i < M; ++i) R[i] = a.r ? a.r[bb * a.r_stride + i] : 0.0;
+        for (int i = 0; i < M; ++i) R[i] = HASR ? a.r[bb * a.r_stride + i] : 0.0;
         if (a.alpha) {
             // metran.py:262-263, 310-322
             const double *al = a.alpha + bb * a.alpha_stride;
@@ -119,7 +150,14 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a) {
                 q[i] = a.q[bb * a.q_stride + i];
             }
         }
+#pragma unroll
+        for (int i = 0; i < N; ++i) cst[i * 32] = q[i];
+#pragma unroll
+        for (int i = 0; i < M * K; ++i) cst[(N + i) * 32] = G[i];
+        __syncwarp();
     }
+#define MKF_QQ(i) lds_f64(cst + (i) * 32)
+#define MKF_GG(i) lds_f64(cst + (N + (i)) * 32)
 
     // ---- state: x0 = 0, P0 = I (kalmanfilter.py:747-750) ------------------------------
     double x[N], P[NT];
@@ -131,37 +169,41 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a) {
         for (int c = r; c < N; ++c) P[tri<N>(r, c)] = (r == c) ? 1.0 : 0.0;
 
     KahanSum sum_sigma;
-    double fprod = 1.0;   // running product of innovation variances, mantissa in [1,2)
-    int64_t fexp = 0;     // ... and its binary exponent: sum log f = log(fprod) + fexp ln 2
-    int64_t nobs = 0;
+    double fprod = 1.0;  // running product of innovation variances, mantissa in [1,2)
+    int fexp = 0;        // ... and its binary exponent: sum log f = log(fprod) + fexp ln 2
+    int nobs = 0;
     int nsig = 0;
     bool bad = false;
+    bool pend_on = false;  // previous step's contribution, folded one step later
+    double pend_sigma = 0.0, pend_prod = 1.0;
 
     const int64_t T = a.T;
-    const int64_t ntiles = (T + kTT - 1) / kTT;
+    const int64_t ntiles = (T + TT - 1) / TT;
     const double *yb = a.y + bb * a.y_stride;
-    double *myrow = ring + (size_t)lane * PITCH;  // + stage * 32 * PITCH
+    // shared y: the tile holds ONE row that every lane reads (broadcast)
+    double *myrow = ring + ((shared_y && tma) || !active ? 0 : (size_t)lane * PITCH);  // + stage * 32 * PITCH
+    constexpr unsigned kTileBytes = 32u * PITCH * 8u;
 
     auto issue_tile = [&](int64_t tile) {
         if (tile >= ntiles) {
-            if (!bulk) cp_async_commit();
+            if (!tma) cp_async_commit();
             return;
         }
         const int s = (int)(tile % kStages);
-        const int64_t t0 = tile * kTT;
-        const int nel = (int)min((int64_t)kTT, T - t0) * M;
-        double *dst = myrow + (size_t)s * 32 * PITCH;
-        const double *src = yb + t0 * M;
-        if (bulk) {
-            const int nel16 = nel & ~1;  // bulk copies move multiples of 16 bytes
+        const int64_t t0 = tile * TT;
+        double *stage = ring + (size_t)s * 32 * PITCH;
+        if (tma) {
+            // WAR across proxies: the lanes' earlier LDS of this stage vs. the async write
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            if (lane == 0) mbar_arrive_expect_tx(&bars[s], (unsigned)(nactive * nel16 * 8));
             __syncwarp();
-            if (active) {
-                if (nel16) bulk_g2s(dst, src, (unsigned)(nel16 * 8), &bars[s]);
-                if (nel & 1) dst[nel - 1] = src[nel - 1];
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars[s], shared_y ? (unsigned)(PITCH * 8) : kTileBytes);
+                tma_load_2d(stage, &ymap, (int)(t0 * M), shared_y ? 0 : (int)b0, &bars[s]);
             }
         } else {
+            const int nel = (int)min((int64_t)TT, T - t0) * M;
+            double *dst = stage + (size_t)lane * PITCH;
+            const double *src = yb + t0 * M;
             if (active)
                 for (int e = 0; e < nel; ++e) cp_async8(dst + e, src + e);
             cp_async_commit();
@@ -172,19 +214,24 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a) {
     for (int64_t tile = 0; tile < ntiles; ++tile) {
         issue_tile(tile + 1);
         const int s = (int)(tile % kStages);
-        if (bulk) {
+        if (tma) {
             mbar_wait(&bars[s], (unsigned)((tile / kStages) & 1));
         } else {
             cp_async_wait<kStages - 1>();
         }
         const double *ys = myrow + (size_t)s * 32 * PITCH;
-        const int64_t t0 = tile * kTT;
-        const int steps = (int)min((int64_t)kTT, T - t0);
+        const int64_t t0 = tile * TT;
+        const int steps = (int)min((int64_t)TT, T - t0);
+
+        double yv[M], yn[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) yv[i] = ys[i];
 
         for (int tt = 0; tt < steps; ++tt) {
-            double yv[M];
+            // prefetch the next step's observations of this tile (LDS latency off the path)
+            const int tn = (tt + 1 < steps) ? tt + 1 : tt;
 #pragma unroll
-            for (int i = 0; i < M; ++i) yv[i] = ys[tt * M + i];
+            for (int i = 0; i < M; ++i) yn[i] = ys[tn * M + i];
 
             // ---- predict: x = phi x ; P = phi P phi + Q (kalmanfilter.py:318-331) -----
 #pragma unroll
@@ -194,82 +241,184 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a) {
 #pragma unroll
                 for (int c = r; c < N; ++c) {
                     double v = (phi[r] * P[tri<N>(r, c)]) * phi[c];
-                    P[tri<N>(r, c)] = (r == c) ? v + q[r] : v;
+                    P[tri<N>(r, c)] = (r == c) ? v + MKF_QQ(r) : v;
                 }
+            // fold the PREVIOUS step's sigma / product of f into the running sums here, in
+            // the shadow of this step's arithmetic (branch-free: neutral elements when the
+            // previous step does not count)
+            sum_sigma.add(pend_on ? pend_sigma : 0.0);
+            fprod *= pend_on ? pend_prod : 1.0;
+            {
+                const int hi = __double2hiint(fprod);
+                const int ex = ((hi >> 20) & 0x7ff) - 1023;
+                fexp += ex;
+                fprod = __hiloint2double(hi - (ex << 20), __double2loint(fprod));
+            }
 
             // ---- sequential scalar updates (kalmanfilter.py:341-378) -------------------
             double sigma = 0.0, stepprod = 1.0;
             int cnt = 0;
+            bool all_obs = true;
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                if (is_observed(yv[i])) {
-                    ++cnt;
+            for (int i = 0; i < M; ++i) all_obs = all_obs && is_observed(yv[i]);
+            if (__all_sync(0xffffffffu, all_obs)) {
+                // Dense step, straight-line code with one-series look-ahead: while the
+                // reciprocal of f_i is in flight, e = P h_{i+1} and s = h_{i+1}.d_i are
+                // computed from the NOT yet updated P; afterwards
+                //   d_{i+1} = (P - g d^T) h_{i+1} = e - g s
+                // which is the same vector the reference gets from the updated P.
+                cnt = M;
+                double d[N], e[N], gc[K + 1], gn[K + 1];
+#pragma unroll
+                for (int j = 0; j < K; ++j) gc[j] = MKF_GG(j);
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    double s = P[sym<N>(r, 0)];
+#pragma unroll
+                    for (int j = 0; j < K; ++j) s = fma(gc[j], P[sym<N>(r, M + j)], s);
+                    d[r] = s;
+                }
+                double f = HASR ? d[0] + R[0] : d[0];
+#pragma unroll
+                for (int j = 0; j < K; ++j) f = fma(gc[j], d[M + j], f);
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    const double rf = rcp_nr(f);
+                    bad = bad || f_is_bad(f);
+                    stepprod *= f;
+                    double snext = 0.0;
+                    if (i + 1 < M) {
+#pragma unroll
+                        for (int j = 0; j < K; ++j) gn[j] = MKF_GG((i + 1) * K + j);
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            double s = P[sym<N>(r, i + 1)];
+#pragma unroll
+                            for (int j = 0; j < K; ++j) s = fma(gn[j], P[sym<N>(r, M + j)], s);
+                            e[r] = s;
+                        }
+                        snext = d[i + 1];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) snext = fma(gn[j], d[M + j], snext);
+                    }
                     double v = yv[i] - x[i];
 #pragma unroll
-                    for (int j = 0; j < K; ++j) v = fma(-G[i * K + j], x[M + j], v);
-                    double d[N];
+                    for (int j = 0; j < K; ++j) v = fma(-gc[j], x[M + j], v);
+                    double g[N];
+#pragma unroll
+                    for (int r = 0; r < N; ++r) g[r] = d[r] * rf;
 #pragma unroll
                     for (int r = 0; r < N; ++r) {
-                        double s = P[sym<N>(r, i)];
+                        x[r] = fma(g[r], v, x[r]);
 #pragma unroll
-                        for (int j = 0; j < K; ++j) s = fma(G[i * K + j], P[sym<N>(r, M + j)], s);
-                        d[r] = s;
-                    }
-                    double f = d[i] + R[i];
-#pragma unroll
-                    for (int j = 0; j < K; ++j) f = fma(G[i * K + j], d[M + j], f);
-                    const double rf = 1.0 / f;
-                    if (!(f > 0.0) || !isfinite(f)) bad = true;
-#pragma unroll
-                    for (int r = 0; r < N; ++r) {
-                        const double g = d[r] * rf;
-                        x[r] = fma(g, v, x[r]);
-#pragma unroll
-                        for (int c = r; c < N; ++c) P[tri<N>(r, c)] = fma(-g, d[c], P[tri<N>(r, c)]);
+                        for (int c = r; c < N; ++c) P[tri<N>(r, c)] = fma(-g[r], d[c], P[tri<N>(r, c)]);
                     }
                     sigma = fma(v * v, rf, sigma);
-                    stepprod *= f;
+                    if (i + 1 < M) {
+#pragma unroll
+                        for (int r = 0; r < N; ++r) d[r] = fma(-g[r], snext, e[r]);
+                        f = HASR ? d[i + 1] + R[i + 1] : d[i + 1];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            f = fma(gn[j], d[M + j], f);
+                            gc[j] = gn[j];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    if (is_observed(yv[i])) {
+                        ++cnt;
+                        double gc[K + 1];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) gc[j] = MKF_GG(i * K + j);
+                        double v = yv[i] - x[i];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) v = fma(-gc[j], x[M + j], v);
+                        double d[N];
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            double s = P[sym<N>(r, i)];
+#pragma unroll
+                            for (int j = 0; j < K; ++j) s = fma(gc[j], P[sym<N>(r, M + j)], s);
+                            d[r] = s;
+                        }
+                        double f = HASR ? d[i] + R[i] : d[i];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) f = fma(gc[j], d[M + j], f);
+                        const double rf = rcp_nr(f);
+                        bad = bad || f_is_bad(f);
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            const double g = d[r] * rf;
+                            x[r] = fma(g, v, x[r]);
+#pragma unroll
+                            for (int c = r; c < N; ++c) P[tri<N>(r, c)] = fma(-g, d[c], P[tri<N>(r, c)]);
+                        }
+                        sigma = fma(v * v, rf, sigma);
+                        stepprod *= f;
+                    }
                 }
             }
-            if (cnt > 0) {
-                if (nsig >= a.warmup) {
-                    sum_sigma.add(sigma);
-                    // fold the step's product of f into (fprod, fexp) and renormalise
-                    fprod *= stepprod;
-                    const int hi = __double2hiint(fprod);
-                    const int ex = ((hi >> 20) & 0x7ff) - 1023;
-                    fexp += ex;
-                    fprod = __hiloint2double(hi - (ex << 20), __double2loint(fprod));
-                }
-                ++nsig;
-            }
-            if (t0 + tt >= a.warmup) nobs += cnt;
+            // quirk Q4 (kalmanfilter.py:563-566): the first `warmup` OBSERVED steps are
+            // dropped from the sums, nobs counts raw steps t >= warmup
+            pend_on = (cnt > 0) && (nsig >= a.warmup);
+            pend_sigma = sigma;
+            pend_prod = stepprod;
+            nsig += (cnt > 0) ? 1 : 0;
+            nobs += (t0 + tt >= a.warmup) ? cnt : 0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) yv[i] = yn[i];
         }
     }
-    if (!bulk) cp_async_wait<0>();
+    if (!tma) cp_async_wait<0>();
+#undef MKF_QQ
+#undef MKF_GG
 
+    sum_sigma.add(pend_on ? pend_sigma : 0.0);
+    fprod *= pend_on ? pend_prod : 1.0;
     if (active) {
         double logdet = log(fprod) + (double)fexp * kLn2;
         double mle = (double)nobs * kLog2Pi + logdet + sum_sigma.value();
         if (bad) mle = nan("");
         a.mle[b] = mle;
-        if (a.nobs) a.nobs[b] = nobs;
+        if (a.nobs) a.nobs[b] = (int64_t)nobs;
         if (a.status) a.status[b] = bad ? MKF_STATUS_NONPOSITIVE_F : 0;
     }
 }
 
-template <int M, int K>
-int launch(const DfmArgs &a, cudaStream_t stream) {
-    auto kern = dfm_loglik_kernel<M, K>;
-    const size_t smem = smem_bytes(M);
+// Builds the tensor map of y viewed as [rows][row_elems] doubles (defined in filter_dfm.cu).
+int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
+                      int box_rows, int box_elems);
+
+template <int M, int K, bool HASR>
+int launch_r(const DfmArgs &a0, cudaStream_t stream) {
+    DfmArgs a = a0;
+    alignas(64) CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    constexpr int TT = tile_steps(M);
+    if (a.use_tma) {
+        const bool shared_y = a.y_stride == 0;
+        int rc = make_y_tensor_map(&map, a.y, shared_y ? 1 : a.B, a.T * M, shared_y ? a.T * M : a.y_stride,
+                                   shared_y ? 1 : 32, TT * M);
+        if (rc != MKF_OK) a.use_tma = 0;  // cp.async staging instead
+    }
+    auto kern = dfm_loglik_kernel<M, K, HASR>;
+    const size_t smem = smem_bytes(M, K);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         mkf_host::set_cuda_error(e);
         return MKF_ERR_CUDA;
     }
     const int64_t blocks = (a.B + kBlock - 1) / kBlock;
-    kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a);
+    kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
     return mkf_host::check_launch();
+}
+
+template <int M, int K>
+int launch(const DfmArgs &a, cudaStream_t stream) {
+    return a.r ? launch_r<M, K, true>(a, stream) : launch_r<M, K, false>(a, stream);
 }
 
 // one translation unit per K instantiates M = 1..8 (keeps nvcc wall time parallel)

@@ -14,7 +14,7 @@ def timeit(fn, reps=5):
         ts.append(e0.elapsed_time(e1))
     return min(ts), float(np.median(ts))
 m, k = 5, 3; n = m + k
-for B, T in ((1024, 2000), (8192, 2000), (32768, 5000), (65536, 2000)):
+for B, T in ((1024, 2000), (8192, 2000), (32768, 5000), (37888, 5000), (18944, 5000), (75776, 2000)):
     g = torch.Generator(device=dev); g.manual_seed(1)
     y = torch.randn(B, T, m, dtype=torch.float64, device=dev, generator=g)
     alpha = torch.rand(B, n, dtype=torch.float64, device=dev, generator=g) * 45 + 5
@@ -28,19 +28,13 @@ for B, T in ((1024, 2000), (8192, 2000), (32768, 5000), (65536, 2000)):
         tmin, tmed = timeit(lambda: eng.filter_loglik(y, A, Q, H, R, flags=3))
         print(f"generic  B={B} T={T}: min {tmin:.3f} ms -> {B*T/tmin*1e3:.3e} ts*models/s", flush=True)
     del y
-# C3-shaped: n=32 m=64
-B, T, n, m = 256, 1000, 32, 64
-g = torch.Generator(device=dev); g.manual_seed(2)
+
+# missing-data path
+B, T = 32768, 2000
+g = torch.Generator(device=dev); g.manual_seed(1)
 y = torch.randn(B, T, m, dtype=torch.float64, device=dev, generator=g)
-phi = torch.rand(B, n, dtype=torch.float64, device=dev, generator=g) * 0.2 + 0.75
-A = torch.diag_embed(phi); Q = torch.diag_embed(1 - phi**2)
-H = torch.randn(B, m, n, dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
-R = torch.full((B, m), 0.1, dtype=torch.float64, device=dev)
-tmin, _ = timeit(lambda: eng.filter_loglik(y, A, Q, H, R, flags=3), reps=3)
-print(f"generic n32 m64 loglik B={B} T={T}: {tmin:.2f} ms -> {B*T/tmin*1e3:.3e}", flush=True)
-out = eng.filter_history(y, A, Q, H, R, flags=3)
-tmin, _ = timeit(lambda: eng.filter_history(y, A, Q, H, R, flags=3), reps=3)
-print(f"generic n32 m64 history B={B} T={T}: {tmin:.2f} ms -> {B*T/tmin*1e3:.3e}", flush=True)
-tmin, _ = timeit(lambda: eng.smoother(out['fm'], out['fc'], out['pm'], out['pc'], A, flags=3), reps=3)
-print(f"smoother n32 B={B} T={T}: {tmin:.2f} ms -> {B*T/tmin*1e3:.3e}", flush=True)
-import os; print("cores", len(os.sched_getaffinity(0)), os.cpu_count())
+y[torch.rand(B, T, m, device=dev, generator=g) < 0.5] = float("nan")
+alpha = torch.rand(B, n, dtype=torch.float64, device=dev, generator=g) * 45 + 5
+G = (torch.rand(B, m, k, dtype=torch.float64, device=dev, generator=g) * 0.6 + 0.3) / np.sqrt(k)
+tmin, tmed = timeit(lambda: eng.dfm_loglik_alpha(y, alpha, G))
+print(f"dfm_alpha 50% missing B={B} T={T}: min {tmin:.3f} ms -> {B*T/tmin*1e3:.3e} ts*models/s", flush=True)
