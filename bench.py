@@ -7,8 +7,8 @@ One "step" = one pass of the hot path (mkf_dfm_loglik_alpha: parameter map + seq
 Kalman filter + -2 log L per model, then the deterministic batch reduction and, for
 N > 1, the NCCL all-reduce of the pooled objective) over one batch of synthetic models.
 Default workload ("metric", BASELINE.json `metric`): state_dim 8 (5 series + 3 common
-factors), T = 5000, 32768 independent models per GPU (C4's per-GPU shard size), weak
-scaling.  Under torchrun each rank owns one GPU and its own shard; the time of the K
+factors), T = 5000, 37888 independent models per GPU (148 SMs x 8 warps x 32 lanes: one
+full wave of the thread-per-model kernel), weak scaling.  Under torchrun each rank owns one GPU and its own shard; the time of the K
 steps is the max over ranks.
 
 `--impl reference` times the CPU restatement of the reference's algorithm (oracle/, the
@@ -32,10 +32,12 @@ UNIT = "timesteps*models/s"
 
 CONFIGS = {
     # name: (models per GPU, T, m series, k common factors, missing fraction)
-    "metric": (32768, 5000, 5, 3, 0.0),
-    "c1": (1024, 2000, 5, 3, 0.0),
-    "c4": (32768, 10000, 5, 3, 0.0),
-    "metric_miss50": (32768, 5000, 5, 3, 0.5),
+    # "metric": BASELINE.json's headline shape (state_dim 8, T = 5000); 37888 models per GPU
+    # = 148 SMs x 8 resident warps x 32 lanes, one full wave of the thread-per-model kernel
+    "metric": (37888, 5000, 5, 3, 0.0),
+    "c1": (1024, 2000, 5, 3, 0.0),            # BASELINE.json configs[1]
+    "c4": (32768, 10000, 5, 3, 0.0),          # configs[4]: 262144 models over 8 GPUs
+    "metric_miss50": (37888, 5000, 5, 3, 0.5),
 }
 
 
