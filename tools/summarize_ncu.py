@@ -80,9 +80,10 @@ def main():
         n += 1
     total = sum(v[1] for v in tot.values())
     with open("profiles/%s_launches_summary.md" % tag, "w") as fh:
-        fh.write("# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu`\n\n" % tag)
-        fh.write("(`ncu --metrics gpu__time_duration.sum --clock-control none -c 400`; cold-cache, serialised: "
-                 "compare shares, not absolutes; includes the torch kernels that GENERATE the synthetic y)\n\n")
+        fh.write("# %s: ncu launch list of `python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu`\n\n" % tag)
+        fh.write("(`ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400`; "
+                 "bench.py brackets warm-up + timed steps with cudaProfilerStart/Stop so the torch kernels that "
+                 "generate the synthetic y are excluded; cold-cache, serialised: compare shares, not absolutes)\n\n")
         fh.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for name, (c, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:25]:
             fh.write("| `%s` | %d | %.3f | %.1f %% |\n" % (name[:90], c, ms, 100 * ms / total))
