@@ -185,7 +185,7 @@ def cpu_baseline(cfg, threads=0, seed=99):
                     if 1 <= c <= ncpu})
     if threads:
         cands = [threads]
-    Bs = max(48 * (int(quota) if quota else ncpu), 256)
+    Bs = min(max(256 * (int(quota) if quota else ncpu), 1024), 8192)
     rng = np.random.default_rng(seed)
     alpha, gamma = make_params(rng, Bs, m, k)
     y = simulate_cpu(rng, alpha, gamma, T, miss)
