@@ -353,7 +353,14 @@ def main():
 
         need = B * T * m * 8
         Be = B
-        while Be > 1024 and need * Be // B > 0.2 * psutil.virtual_memory().available / max(world, 1):
+        avail = psutil.virtual_memory().available
+        try:                                  # cgroup memory limit of the container, if any
+            lim = open("/sys/fs/cgroup/memory.max").read().strip()
+            if lim != "max":
+                avail = min(avail, int(lim))
+        except Exception:
+            pass
+        while Be > 1024 and need * Be // B > 0.2 * avail / max(world, 1):
             Be //= 2
         y_host = torch.empty(Be, T, m, dtype=torch.float64).pin_memory()
         y_host.copy_(y[:Be])
