@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
             }
 
             // ---- sequential update over observed series (kalmanfilter.py:335-382) ----
-            double sigma = 0.0, detf = 0.0;
+            double sigma = 0.0, fman = 1.0;
+            int fexp = 0, bad_step = 0;
             int cnt = 0;
             for (int j0 = 0; j0 < m; j0 += NP) {
                 const int jj = j0 + r;
@@ -211,7 +212,10 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
                         }
                     }
                     const double f = sR[j] + group_sum<NP>(h_r * d);
-                    const double g = d / f;
+                    // one reciprocal serves k = d/f and v^2/f; f <= 0 or non-finite is flagged
+                    // and poisons the result like the reference's log(f) (kalmanfilter.py:378)
+                    const double rf = f_is_bad(f) ? nan("") : rcp_nr(f);
+                    const double g = d * rf;
                     sx[r] = g;
                     __syncwarp(gmask);
 #pragma unroll
@@ -222,11 +226,20 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
                     }
                     __syncwarp(gmask);
                     x = fma(g, v, x);
-                    sigma += v * v / f;
-                    detf += log(f);
-                    if (!(f > 0.0) || !isfinite(f)) status |= MKF_STATUS_NONPOSITIVE_F;
+                    sigma = fma(v * v, rf, sigma);
+                    // sum log f as log(prod f): mantissa product + binary exponent, one log per step
+                    fman *= f;
+                    {
+                        const int hi = __double2hiint(fman);
+                        const int ex = ((hi >> 20) & 0x7ff) - 1023;
+                        fexp += ex;
+                        fman = __hiloint2double(hi - (ex << 20), __double2loint(fman));
+                    }
+                    if (f_is_bad(f)) status |= MKF_STATUS_NONPOSITIVE_F;
                 }
             }
+            (void)bad_step;
+            const double detf = (cnt > 0) ? log(fman) + (double)fexp * kLn2 : 0.0;
             if (cnt > 0) {
                 if (nsig >= a.warmup) {
                     sum_sigma.add(sigma);

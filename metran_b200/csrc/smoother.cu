@@ -38,7 +38,7 @@ struct SmootherArgs {
 };
 
 template <int NP>
-__global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
+__global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const SmootherArgs a) {
     extern __shared__ __align__(16) double smem[];
     constexpr int LD = NP + 2;  // padded leading dimension (even: rows stay double2-aligned)
     const int n = a.n;
@@ -50,10 +50,14 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
     if (b >= a.B) return;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
 
+    // Only one n-vector of registers is live at a time (L, then z, then M); every matrix
+    // that must survive a phase lives in shared memory, rows owned by lanes.
     double *sm_ = smem + (size_t)group_in_block * a.smem_model;
     double *sL = sm_;   sm_ += NP * LD;   // Cholesky factor, row-major
     double *sD = sm_;   sm_ += NP * LD;   // P_s[t+1] - P_p[t+1]
-    double *sG = sm_;   sm_ += NP * LD;   // smoothing gain
+    double *sG = sm_;   sm_ += NP * LD;   // smoothing gain G_t
+    double *sPs = sm_;  sm_ += NP * LD;   // P_s[t+1] (rows), carried between steps
+    double *sPf = sm_;  sm_ += NP * LD;   // P_f[t]
     double *sv = sm_;   sm_ += NP;        // broadcast vector
     double *sa = sm_;   sm_ += NP;        // diag(A)
     double *sinv = sm_; sm_ += NP;        // 1 / L_ii
@@ -66,7 +70,6 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
             int rr = i / NP, c = i % NP;
             sA[rr * LD + c] = (rr < n && c < n) ? Ab[rr * n + c] : 0.0;
         }
-    __syncwarp(gmask);
 
     const int64_t T = a.T;
     const int64_t base = b * T;
@@ -75,23 +78,22 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
 
     // t = T-1: smoothed = filtered (kalmanfilter.py:450-451)
     double xs = rv ? a.fm[(base + T - 1) * n + r] : 0.0;
-    double Ps[NP];
     {
         const double *src = a.fc + (base + T - 1) * n * n + r;
+        double *dst = a.sc + (base + T - 1) * n * n + r;
 #pragma unroll
-        for (int c = 0; c < NP; ++c) Ps[c] = (rv && c < n) ? src[(int64_t)c * n] : 0.0;
-        if (rv) {
-            a.sm[(base + T - 1) * n + r] = xs;
-            double *dst = a.sc + (base + T - 1) * n * n + r;
-#pragma unroll
-            for (int c = 0; c < NP; ++c)
-                if (c < n) dst[(int64_t)c * n] = Ps[c];
+        for (int c = 0; c < NP; ++c) {
+            const double v = (rv && c < n) ? src[(int64_t)c * n] : 0.0;
+            sPs[r * LD + c] = v;
+            if (rv && c < n) dst[(int64_t)c * n] = v;
         }
+        if (rv) a.sm[(base + T - 1) * n + r] = xs;
     }
+    __syncwarp(gmask);
 
     for (int64_t t = T - 2; t >= 0; --t) {
-        // ---- loads ---------------------------------------------------------------------
-        double L[NP];  // starts as row r of P_p[t+1], becomes row r of its Cholesky factor
+        // ---- P_p[t+1] row, D = P_s[t+1] - P_p[t+1], delta ------------------------------------
+        double L[NP];  // row r of P_p[t+1], becomes row r of its Cholesky factor
         {
             const double *src = a.pc + (base + t + 1) * n * n + r;
 #pragma unroll
@@ -99,16 +101,12 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
         }
         const double xp = rv ? a.pm[(base + t + 1) * n + r] : 0.0;
         const double xf = rv ? a.fm[(base + t) * n + r] : 0.0;
-        double Pf[NP];
-        {
-            const double *src = a.fc + (base + t) * n * n + r;
 #pragma unroll
-            for (int c = 0; c < NP; ++c) Pf[c] = (rv && c < n) ? src[(int64_t)c * n] : 0.0;
+        for (int c = 0; c < NP; c += 2) {
+            const double2 ps = *reinterpret_cast<const double2 *>(sPs + r * LD + c);
+            const double p0 = (rv && c < n) ? L[c] : 0.0, p1 = (rv && c + 1 < n) ? L[c + 1] : 0.0;
+            *reinterpret_cast<double2 *>(sD + r * LD + c) = make_double2(ps.x - p0, ps.y - p1);
         }
-        // D = P_s[t+1] - P_p[t+1] -> shared; delta = x_s[t+1] - x_p[t+1]
-#pragma unroll
-        for (int c = 0; c < NP; c += 2)
-            *reinterpret_cast<double2 *>(sD + r * LD + c) = make_double2(Ps[c] - L[c], Ps[c + 1] - L[c + 1]);
         const double delta = xs - xp;
 
         // ---- Cholesky P_p = L L^T (padded rows/cols are the identity) ---------------------
@@ -116,8 +114,8 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
         for (int j = 0; j < NP; ++j) {
             const double pjj = __shfl_sync(gmask, L[j], j, NP);
             if (!(pjj > 0.0)) status |= MKF_STATUS_CHOL_FAILED;
-            const double ljj = sqrt(pjj);
-            const double inv = 1.0 / ljj;
+            const double inv = rsqrt(pjj);
+            const double ljj = pjj * inv;
             const double lrj = (r == j) ? ljj : ((r > j) ? L[j] * inv : 0.0);
             L[j] = lrj;
             if (r == j) sinv[j] = inv;
@@ -134,20 +132,28 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
             *reinterpret_cast<double2 *>(sL + r * LD + c) =
                 make_double2((c <= r) ? L[c] : 0.0, (c + 1 <= r) ? L[c + 1] : 0.0);
         sv[r] = delta;
-        __syncwarp(gmask);
 
         // ---- lane c: solve (L L^T) g = (A P_f)[:, c]  ->  g = row c of G ----------------
         double z[NP];
+        {
+            const double *src = a.fc + (base + t) * n * n + r;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) z[i] = (rv && i < n) ? src[(int64_t)i * n] : 0.0;
+#pragma unroll
+            for (int i = 0; i < NP; i += 2)
+                *reinterpret_cast<double2 *>(sPf + r * LD + i) = make_double2(z[i], z[i + 1]);
+        }
+        __syncwarp(gmask);
         if (diagA) {
 #pragma unroll
-            for (int i = 0; i < NP; ++i) z[i] = sa[i] * Pf[i];
+            for (int i = 0; i < NP; ++i) z[i] *= sa[i];
         } else {
 #pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                double s = 0.0;
+            for (int i = 0; i < NP; ++i) z[i] = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double pk = sPf[r * LD + k];
 #pragma unroll
-                for (int k = 0; k < NP; ++k) s = fma(sA[i * LD + k], Pf[k], s);
-                z[i] = s;
+                for (int i = 0; i < NP; ++i) z[i] = fma(sA[i * LD + k], pk, z[i]);
             }
         }
 #pragma unroll
@@ -177,40 +183,40 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmootherArgs a) {
             *reinterpret_cast<double2 *>(sG + r * LD + i) = make_double2(z[i], z[i + 1]);
         __syncwarp(gmask);
 
-        // ---- M = G D (row r), then P_s[t] = P_f + M G^T ---------------------------------
+        // ---- M = G D (row r) -----------------------------------------------------------------
         double Mrow[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) Mrow[j] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
+        for (int k = 0; k < n; ++k) {
+            const double zk = sG[r * LD + k];
 #pragma unroll
             for (int j = 0; j < NP; j += 2) {
                 double2 dk = *reinterpret_cast<const double2 *>(sD + k * LD + j);
-                Mrow[j] = fma(z[k], dk.x, Mrow[j]);
-                Mrow[j + 1] = fma(z[k], dk.y, Mrow[j + 1]);
+                Mrow[j] = fma(zk, dk.x, Mrow[j]);
+                Mrow[j + 1] = fma(zk, dk.y, Mrow[j + 1]);
             }
         }
+        __syncwarp(gmask);  // all reads of sPs/sD done before sPs is rewritten
+        // ---- P_s[t] = P_f + M G^T : element (r, j), stored column-per-lane ----------------
+        double *dst = a.sc + (base + t) * n * n + r;
+        for (int j = 0; j < n; ++j) {
+            double s0 = sPf[r * LD + j], s1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NP; ++j) {
-            double s = Pf[j];
-#pragma unroll
-            for (int k = 0; k < NP; k += 2) {
-                double2 gj = *reinterpret_cast<const double2 *>(sG + j * LD + k);
-                s = fma(Mrow[k], gj.x, s);
-                s = fma(Mrow[k + 1], gj.y, s);
+            for (int k = 0; k < NP; k += 4) {
+                double2 g0 = *reinterpret_cast<const double2 *>(sG + j * LD + k);
+                double2 g1 = *reinterpret_cast<const double2 *>(sG + j * LD + k + 2);
+                s0 = fma(Mrow[k], g0.x, s0);
+                s1 = fma(Mrow[k + 1], g0.y, s1);
+                s0 = fma(Mrow[k + 2], g1.x, s0);
+                s1 = fma(Mrow[k + 3], g1.y, s1);
             }
-            Ps[j] = s;
+            const double s = s0 + s1;
+            sPs[r * LD + j] = s;
+            if (rv) dst[(int64_t)j * n] = s;
         }
         xs = xnew;
+        if (rv) a.sm[(base + t) * n + r] = xs;
         __syncwarp(gmask);  // shared buffers are rewritten next step
-
-        if (rv) {
-            a.sm[(base + t) * n + r] = xs;
-            double *dst = a.sc + (base + t) * n * n + r;
-#pragma unroll
-            for (int c = 0; c < NP; ++c)
-                if (c < n) dst[(int64_t)c * n] = Ps[c];
-        }
     }
     if (r == 0 && a.status) a.status[b] = status;
 }
@@ -219,7 +225,7 @@ template <int NP>
 int launch_smoother(SmootherArgs a, cudaStream_t stream) {
     constexpr int LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    int per = 3 * NP * LD + 3 * NP + (diagA ? 0 : NP * LD);
+    int per = 5 * NP * LD + 3 * NP + (diagA ? 0 : NP * LD);
     per = (per + 1) & ~1;
     a.smem_model = per;
     int threads = (NP == 32) ? 64 : 128;
