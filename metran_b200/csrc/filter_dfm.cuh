@@ -258,10 +258,17 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             // ---- sequential scalar updates (kalmanfilter.py:341-378) -------------------
             double sigma = 0.0, stepprod = 1.0;
             int cnt = 0;
-            bool all_obs = true;
+            bool all_obs = true, any_obs = false;
 #pragma unroll
-            for (int i = 0; i < M; ++i) all_obs = all_obs && is_observed(yv[i]);
-            if (__all_sync(0xffffffffu, all_obs)) {
+            for (int i = 0; i < M; ++i) {
+                const bool o = is_observed(yv[i]);
+                all_obs = all_obs && o;
+                any_obs = any_obs || o;
+            }
+            if (!__any_sync(0xffffffffu, any_obs)) {
+                // nobody in the warp observes anything at this step (irregular sampling on a
+                // daily grid: 94.5 % of the steps of the reference's example data): predict only
+            } else if (__all_sync(0xffffffffu, all_obs)) {
                 // Dense step, straight-line code with one-series look-ahead: while the
                 // reciprocal of f_i is in flight, e = P h_{i+1} and s = h_{i+1}.d_i are
                 // computed from the NOT yet updated P; afterwards

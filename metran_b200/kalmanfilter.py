@@ -117,6 +117,24 @@ def _filter_device(engine, y_dev, A, Q, H, R, x0, P0, covariances=True):
                                  flags=_structure_flags(A, Q), covariances=covariances)
 
 
+class _LazyHistory:
+    """Device-resident filter/smoother history; arrays are copied to the host on first read.
+
+    An objective evaluation through the reference facade (Metran.get_mle, metran.py:605-622)
+    only ever reads sigmas/detfs; the [T,n,n] covariances cross PCIe only when a getter asks.
+    """
+
+    def __init__(self, out):
+        self.out = out
+        self._host = {}
+
+    def get(self, key):
+        if key not in self._host:
+            t = self.out.get(key)
+            self._host[key] = None if t is None else t[0].cpu().numpy()
+        return self._host[key]
+
+
 def _history_to_numpy(out):
     cnt = out["cnt"][0].cpu().numpy()
     seen = cnt > 0
@@ -173,6 +191,11 @@ class SPKalmanFilter:
     """
 
     def __init__(self, engine="cuda", device_engine=None):
+        self._arrays = {}
+        self._lazy = None
+        self._pending = None
+        self._mle_w1 = None
+        self._hist = None
         self.init_states()
         self.detfs = None
         self.sigmas = None
@@ -187,6 +210,10 @@ class SPKalmanFilter:
     # ---------------------------------------------------------------- reference surface
     def init_states(self):
         """Reset state means and covariances (kalmanfilter.py:506-518)."""
+        self._arrays = {k: v for k, v in getattr(self, "_arrays", {}).items() if k in ("sigmas_", "detfs_")}
+        self._lazy = None
+        self._pending = None
+        self._mle_w1 = None
         self.filtered_state_means = None
         self.filtered_state_covariances = None
         self.predicted_state_means = None
@@ -194,6 +221,52 @@ class SPKalmanFilter:
         self.smoothed_state_means = None
         self.smoothed_state_covariances = None
         self._hist = None
+
+    # The six result arrays of the reference are plain attributes there; here they are
+    # properties backed by the device-resident history so that an objective evaluation does
+    # not pay for copying [T,n,n] covariances nobody reads (they are fetched on first access).
+    def _get_array(self, name, key):
+        if name in self._arrays:
+            return self._arrays[name]
+        if key in ("fm", "fc", "pm", "pc"):
+            self._ensure_history()
+        if self._lazy is not None and self._lazy.out.get(key) is not None:
+            self._arrays[name] = self._lazy.get(key)
+            return self._arrays[name]
+        return None
+
+    def _set_array(self, name, value):
+        self._arrays[name] = value
+
+    def _ensure_history(self):
+        if self._hist is None and getattr(self, "_pending", None) is not None:
+            out = self._filter_on_device(*self._pending)
+            cnt = out["cnt"][0].cpu().numpy()
+            seen = cnt > 0
+            self._arrays["sigmas_"] = out["sigma"][0].cpu().numpy()[seen]
+            self._arrays["detfs_"] = out["detf"][0].cpu().numpy()[seen]
+            self._lazy = _LazyHistory(out)
+
+    def _get_series(self, name):
+        if name not in self._arrays:
+            self._ensure_history()
+        return self._arrays.get(name)
+
+    sigmas = property(lambda self: self._get_series("sigmas_"), lambda self, v: self._set_array("sigmas_", v))
+    detfs = property(lambda self: self._get_series("detfs_"), lambda self, v: self._set_array("detfs_", v))
+
+    filtered_state_means = property(lambda self: self._get_array("fm_", "fm"),
+                                    lambda self, v: self._set_array("fm_", v))
+    filtered_state_covariances = property(lambda self: self._get_array("fc_", "fc"),
+                                          lambda self, v: self._set_array("fc_", v))
+    predicted_state_means = property(lambda self: self._get_array("pm_", "pm"),
+                                     lambda self, v: self._set_array("pm_", v))
+    predicted_state_covariances = property(lambda self: self._get_array("pc_", "pc"),
+                                           lambda self, v: self._set_array("pc_", v))
+    smoothed_state_means = property(lambda self: self._get_array("sm_", "sm"),
+                                    lambda self, v: self._set_array("sm_", v))
+    smoothed_state_covariances = property(lambda self: self._get_array("sc_", "sc"),
+                                          lambda self, v: self._set_array("sc_", v))
 
     def set_matrices(self, transition_matrix, transition_covariance, observation_matrix, observation_variance):
         """Set the state-space matrices (kalmanfilter.py:520-548)."""
@@ -204,7 +277,10 @@ class SPKalmanFilter:
         self.nstate = np.int64(self.transition_matrix.shape[0])
 
     def get_mle(self, warmup=1):
-        """-2 log L from the stored sigmas/detfs (kalmanfilter.py:550-567, quirk Q4)."""
+        """-2 log L (kalmanfilter.py:550-567, quirk Q4): the value the log-likelihood kernel
+        produced in run_filter when warmup is the default, else from sigmas/detfs."""
+        if warmup == 1 and getattr(self, "_mle_w1", None) is not None:
+            return self._mle_w1
         detfs = self.detfs[warmup:]
         sigmas = self.sigmas[warmup:]
         nobs = np.sum(self.observation_count[warmup:])
@@ -243,6 +319,19 @@ class SPKalmanFilter:
         if initial_state_covariance is None:
             initial_state_covariance = np.eye(self.nstate)
 
+        self._arrays = {}
+        self._lazy = None
+        self._hist = None
+        self._mle_w1 = None
+        self._pending = None
+        if self.filtermethod == self._filtermethod:
+            # Device path.  What an objective evaluation needs (-2 log L, warmup = 1) is
+            # computed now by the log-likelihood kernel; the history kernel that fills
+            # sigmas/detfs and the state arrays runs only if somebody reads them.
+            self._pending = (np.array(initial_state_mean, dtype=np.float64),
+                             np.array(initial_state_covariance, dtype=np.float64))
+            self._mle_w1 = self._loglik_on_device(*self._pending)
+            return
         (sigmas, detfs, sigmacount, filtered_state_means, filtered_state_covariances,
          predicted_state_means, predicted_state_covariances) = self.filtermethod(
             self.observations, self.transition_matrix, self.transition_covariance,
@@ -260,6 +349,7 @@ class SPKalmanFilter:
         """Filter, then RTS smoother (kalmanfilter.py:676-694); history stays on the device
         between the two kernels."""
         self.run_filter()
+        self._ensure_history()
         eng = self._device_engine()
         h = self._hist
         A = np.ascontiguousarray(self.transition_matrix, dtype=np.float64)
@@ -268,8 +358,11 @@ class SPKalmanFilter:
         if int(status[0]) & _lib.STATUS_CHOL_FAILED:
             logger.warning("Kalman smoother: a predicted covariance is not positive definite.")
         self._hist["sm"], self._hist["sc"] = sm, sc
-        self.smoothed_state_means = sm[0].cpu().numpy()
-        self.smoothed_state_covariances = sc[0].cpu().numpy()
+        self._arrays.pop("sm_", None)
+        self._arrays.pop("sc_", None)
+        if self._lazy is None:
+            self._lazy = _LazyHistory(self._hist)
+        self._lazy.out = self._hist
 
     def simulate(self, observation_matrix, method="smoother"):
         """Projected means and variances (kalmanfilter.py:569-603), one kernel for all t."""
@@ -317,9 +410,43 @@ class SPKalmanFilter:
             return h["sm"], h["sc"]
         return self.smoothed_state_means[None], self.smoothed_state_covariances[None]
 
+    def _loglik_on_device(self, x0, P0):
+        """-2 log L (warmup = 1) of the current matrices: thread-per-model DFM kernel when
+        the model is Metran-shaped (metran.py:283-384) with the default initial state, else
+        the generic kernel."""
+        eng = self._device_engine()
+        if self._y_dev is None:
+            self._y_dev = eng.tensor(unpack_observations(self.observations, self.observation_indices,
+                                                         self.observation_count)[None])
+        A = np.ascontiguousarray(self.transition_matrix, dtype=np.float64)
+        Q = np.ascontiguousarray(self.transition_covariance, dtype=np.float64)
+        H = np.ascontiguousarray(self.observation_matrix, dtype=np.float64)
+        R = np.ascontiguousarray(self.observation_variance, dtype=np.float64)
+        m, n = H.shape
+        flags = _structure_flags(A, Q)
+        dfm = (flags == (_lib.FLAG_A_DIAGONAL | _lib.FLAG_Q_DIAGONAL) and m <= n
+               and eng.dfm_supported(m, n - m) and np.array_equal(H[:, :m], np.eye(m))
+               and not np.any(x0) and np.array_equal(P0, np.eye(n)))
+        if dfm:
+            mle, _, _ = eng.dfm_loglik(self._y_dev, np.diag(A)[None].copy(), np.diag(Q)[None].copy(),
+                                       H[:, m:][None].copy(), r=R[None] if np.any(R) else None)
+        else:
+            mle, _, _ = eng.filter_loglik(self._y_dev, A, Q, H, R, x0=x0[None], P0=P0[None], flags=flags)
+        return float(mle[0])
+
+    def _filter_on_device(self, x0, P0):
+        eng = self._device_engine()
+        if self._y_dev is None:
+            self._y_dev = eng.tensor(unpack_observations(self.observations, self.observation_indices,
+                                                         self.observation_count)[None])
+        out = _filter_device(eng, self._y_dev, self.transition_matrix, self.transition_covariance,
+                             self.observation_matrix, self.observation_variance, x0, P0)
+        self._hist = out
+        return out
+
     def _filtermethod(self, observations, A, Q, H, R, observation_indices, observation_count, x0, P0):
-        """Bound CUDA filtermethod: uses the device-resident observations when the host
-        arrays are the ones set_observations produced."""
+        """Bound CUDA filtermethod with the reference's 9-in / 7-out contract: uses the
+        device-resident observations when the host arrays are the ones set_observations made."""
         eng = self._device_engine()
         if (self._y_dev is not None and observations is self.observations
                 and observation_indices is self.observation_indices
