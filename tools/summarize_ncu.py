@@ -62,7 +62,13 @@ def main():
                    "-k regex:dfm_loglik_kernel python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu",
                    "workload_B_T_m_k": wl, "launches": out}, fh, indent=1)
     with open("profiles/ncu_traffic.json", "w") as fh:
-        json.dump({"workload": wl, "dram_bytes_per_launch": traffic, "from": "profiles/%s_ncu_full_summary.json" % tag}, fh)
+        pipe = None
+        try:
+            pipe = float(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"])
+        except Exception:
+            pass
+        json.dump({"workload": wl, "dram_bytes_per_launch": traffic, "fp64_pipe_active_pct": pipe,
+                   "from": "profiles/%s_ncu_full_summary.json" % tag}, fh)
     # launch list: per-kernel totals and shares
     tot = {}
     n = 0
