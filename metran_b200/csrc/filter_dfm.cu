@@ -30,7 +30,7 @@ int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t r
                       int box_rows, int box_elems) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return MKF_ERR_UNSUPPORTED;
-    if (row_elems <= 0 || rows <= 0 || row_elems >= (1LL << 32) || rows >= (1LL << 32)) return MKF_ERR_UNSUPPORTED;
+    if (row_elems <= 0 || rows <= 0 || row_elems >= (1LL << 31) || rows >= (1LL << 31)) return MKF_ERR_UNSUPPORTED;  // int32 tile coordinates
     if ((row_stride * 8) % 16 != 0 || row_stride * 8 >= (1LL << 40) || row_stride < row_elems) return MKF_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_stride * 8};  // bytes between model rows
