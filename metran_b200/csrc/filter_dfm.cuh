@@ -18,9 +18,12 @@
 // rows x (TT*M) contiguous doubles described by a CUtensorMap over y viewed as [B][T*M] --
 // into a two-stage shared-memory ring (mbarrier complete_tx); lanes read their own row
 // back with LDS.  When the rows are not 16-byte aligned (odd T*M) the kernel stages with
-// 8-byte cp.async instead.  phi stays in registers (80 uses per step); q and Gamma are
-// read from shared memory ([index][lane]) so that the register file is left to P, x and
-// the instruction scheduler.
+// 8-byte cp.async instead.  phi (and Gamma when M*K <= 16) stay in registers; q (and larger
+// Gamma) are read from shared memory ([index][lane]) so that the register file is left to
+// P, x and the instruction scheduler.  A one-series look-ahead variant of the dense step
+// (MKF_LOOKAHEAD=1: d_{i+1} = P h_{i+1} - g_i (d_i.h_{i+1}) computed while 1/f_i is in
+// flight) is kept for reference; it costs 44 more fp64 instructions per step and measured
+// 6 % slower than the plain order on B200 (profiles/r01_microbench_fp64.md).
 #pragma once
 #include <cuda.h>
 #include <string.h>
@@ -47,6 +50,10 @@ struct DfmArgs {
 
 constexpr int kBlock = 32;  // one warp per CTA: CTAs spread evenly over the 592 SMSPs
 constexpr int kStages = 2;
+#ifndef MKF_LOOKAHEAD
+#define MKF_LOOKAHEAD 0
+#endif
+constexpr bool kLookAhead = MKF_LOOKAHEAD != 0;
 
 // time steps per tile: TT*M even (16-byte rows) and, where possible, TT*M = 2 (mod 4) so the
 // 64-bit LDS of a warp (row pitch TT*M doubles) is only 2-way bank conflicted
@@ -121,6 +128,8 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     // ---- per-model constants ---------------------------------------------------------
     double phi[N];
     double R[M];
+    constexpr bool GREG = (M * K <= 16) && (M + K <= 8);   // loadings in registers when they fit
+    double Greg[GREG ? M * K + 1 : 1];
     const int64_t bb = active ? b : b0;  // idle lanes of a ragged last warp shadow its first model
     {
         double q[N], G[M * K + 1];
@@ -154,10 +163,14 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         for (int i = 0; i < N; ++i) cst[i * 32] = q[i];
 #pragma unroll
         for (int i = 0; i < M * K; ++i) cst[(N + i) * 32] = G[i];
+        if (GREG) {
+#pragma unroll
+            for (int i = 0; i < M * K; ++i) Greg[GREG ? i : 0] = G[i];
+        }
         __syncwarp();
     }
 #define MKF_QQ(i) lds_f64(cst + (i) * 32)
-#define MKF_GG(i) lds_f64(cst + (N + (i)) * 32)
+#define MKF_GG(i) (GREG ? Greg[GREG ? (i) : 0] : lds_f64(cst + (N + (i)) * 32))
 
     // ---- state: x0 = 0, P0 = I (kalmanfilter.py:747-750) ------------------------------
     double x[N], P[NT];
@@ -275,6 +288,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 //   d_{i+1} = (P - g d^T) h_{i+1} = e - g s
                 // which is the same vector the reference gets from the updated P.
                 cnt = M;
+                if (kLookAhead) {
                 double d[N], e[N], gc[K + 1], gn[K + 1];
 #pragma unroll
                 for (int j = 0; j < K; ++j) gc[j] = MKF_GG(j);
@@ -330,6 +344,41 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                             f = fma(gn[j], d[M + j], f);
                             gc[j] = gn[j];
                         }
+                    }
+                }
+                } else {
+                    // same arithmetic without the look-ahead (44 fewer fp64 instructions per
+                    // step; the reciprocal chain is hidden by the second warp of the SMSP only)
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        double gc[K + 1];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) gc[j] = MKF_GG(i * K + j);
+                        double v = yv[i] - x[i];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) v = fma(-gc[j], x[M + j], v);
+                        double d[N];
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            double s = P[sym<N>(r, i)];
+#pragma unroll
+                            for (int j = 0; j < K; ++j) s = fma(gc[j], P[sym<N>(r, M + j)], s);
+                            d[r] = s;
+                        }
+                        double f = HASR ? d[i] + R[i] : d[i];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) f = fma(gc[j], d[M + j], f);
+                        const double rf = rcp_nr(f);
+                        bad = bad || f_is_bad(f);
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            const double g = d[r] * rf;
+                            x[r] = fma(g, v, x[r]);
+#pragma unroll
+                            for (int c = r; c < N; ++c) P[tri<N>(r, c)] = fma(-g, d[c], P[tri<N>(r, c)]);
+                        }
+                        sigma = fma(v * v, rf, sigma);
+                        stepprod *= f;
                     }
                 }
             } else {
