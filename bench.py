@@ -134,7 +134,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -143,6 +143,22 @@ class ClockSampler(threading.Thread):
         sm = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": sm, "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+def pin_to_gpu_numa_node(index):
+    """Restrict this process to the CPUs NVML reports as local to the GPU (best effort)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
 
 
 def physical_gpu_index(local_rank):
@@ -284,6 +300,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    orig_affinity = os.sched_getaffinity(0)
+    pin_to_gpu_numa_node(physical_gpu_index(local_rank))   # pinned-memory H2D stays on the GPU's socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -433,6 +451,7 @@ def main():
 
     cpu = None
     if not args.no_cpu:
+        os.sched_setaffinity(0, orig_affinity)
         cb = cpu_baseline(cfg)
         dt, mle_cpu = cb["run"]()
         cpu = {"value": cb["Bs"] * cb["Ts"] / dt, "unit": UNIT, "cores": cb["cores"], "kind": "port",

@@ -40,3 +40,19 @@ e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=T
 e0.record(); eng.dfm_loglik_alpha(mdl_y, d, G); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print("C2: 8192 draws x T=6255 (real C0 data, 94.5%% empty days): %.3f ms -> %.3e ts*models/s" % (ms, 8192 * 6255 / ms * 1e3))
+# K2 (warp-group) vs K1 (thread-per-model) at tiny batch sizes on the C0 data
+import torch
+for Bt in (1, 7, 28, 64):
+    P = np.tile(p, (Bt, 1)) * (1 + 0.01 * np.arange(Bt))[:, None]
+    mats = [mdl._get_matrices(pp) for pp in P]
+    A4, Q4, H4, R4 = (eng.tensor(np.stack([mm[i] for mm in mats])) for i in range(4))
+    Pd = eng.tensor(P)
+    def t_of(fn):
+        fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): fn()
+        e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / 10
+    k1 = t_of(lambda: eng.dfm_loglik_alpha(mdl_y, Pd, G))
+    k2 = t_of(lambda: eng.filter_loglik(mdl_y, A4, Q4, H4, R4, flags=3))
+    print("B=%d on C0 data: K1 %.3f ms, K2 %.3f ms (kernel only)" % (Bt, k1, k2))
