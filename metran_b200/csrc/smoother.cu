@@ -91,16 +91,45 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
     }
     __syncwarp(gmask);
 
+    // For NP <= 8 the inputs of step t-1 are fetched into registers while step t computes
+    // (global-load latency off the critical path); at NP >= 16 the extra registers spill.
+    constexpr bool PREFETCH = NP <= 8;
+    constexpr int NPF = PREFETCH ? NP : 1;
+    double nL[NPF], nF[NPF], nxp = 0.0, nxf = 0.0;
+    auto fetch = [&](int64_t t, double *Lr, double *Fr, double &xp_, double &xf_) {
+        const double *srcp = a.pc + (base + t + 1) * n * n + r;
+        const double *srcf = a.fc + (base + t) * n * n + r;
+#pragma unroll
+        for (int c = 0; c < NPF; ++c) {
+            Lr[c] = (rv && c < n) ? srcp[(int64_t)c * n] : ((c == r) ? 1.0 : 0.0);
+            Fr[c] = (rv && c < n) ? srcf[(int64_t)c * n] : 0.0;
+        }
+        xp_ = rv ? a.pm[(base + t + 1) * n + r] : 0.0;
+        xf_ = rv ? a.fm[(base + t) * n + r] : 0.0;
+    };
+    if (PREFETCH && T >= 2) fetch(T - 2, nL, nF, nxp, nxf);
+
     for (int64_t t = T - 2; t >= 0; --t) {
         // ---- P_p[t+1] row, D = P_s[t+1] - P_p[t+1], delta ------------------------------------
         double L[NP];  // row r of P_p[t+1], becomes row r of its Cholesky factor
-        {
+        double Fcur[NPF];
+        double xp, xf;
+        if (PREFETCH) {
+#pragma unroll
+            for (int c = 0; c < NPF; ++c) {
+                L[c] = nL[c];
+                Fcur[c] = nF[c];
+            }
+            xp = nxp;
+            xf = nxf;
+            if (t > 0) fetch(t - 1, nL, nF, nxp, nxf);
+        } else {
             const double *src = a.pc + (base + t + 1) * n * n + r;
 #pragma unroll
             for (int c = 0; c < NP; ++c) L[c] = (rv && c < n) ? src[(int64_t)c * n] : ((c == r) ? 1.0 : 0.0);
+            xp = rv ? a.pm[(base + t + 1) * n + r] : 0.0;
+            xf = rv ? a.fm[(base + t) * n + r] : 0.0;
         }
-        const double xp = rv ? a.pm[(base + t + 1) * n + r] : 0.0;
-        const double xf = rv ? a.fm[(base + t) * n + r] : 0.0;
 #pragma unroll
         for (int c = 0; c < NP; c += 2) {
             const double2 ps = *reinterpret_cast<const double2 *>(sPs + r * LD + c);
@@ -138,7 +167,8 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
         {
             const double *src = a.fc + (base + t) * n * n + r;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) z[i] = (rv && i < n) ? src[(int64_t)i * n] : 0.0;
+            for (int i = 0; i < NP; ++i)
+                z[i] = PREFETCH ? Fcur[PREFETCH ? i : 0] : ((rv && i < n) ? src[(int64_t)i * n] : 0.0);
 #pragma unroll
             for (int i = 0; i < NP; i += 2)
                 *reinterpret_cast<double2 *>(sPf + r * LD + i) = make_double2(z[i], z[i + 1]);
