@@ -18,8 +18,8 @@
 // rows x (TT*M) contiguous doubles described by a CUtensorMap over y viewed as [B][T*M] --
 // into a two-stage shared-memory ring (mbarrier complete_tx); lanes read their own row
 // back with LDS.  When the rows are not 16-byte aligned (odd T*M) the kernel stages with
-// 8-byte cp.async instead.  phi (and Gamma when M*K <= 16) stay in registers; q (and larger
-// Gamma) are read from shared memory ([index][lane]) so that the register file is left to
+// 8-byte cp.async instead.  phi (and q, Gamma when M*K <= 16, n <= 8) stay in registers; for
+// larger shapes q and Gamma are read from shared memory ([index][lane]) so that the register file is left to
 // P, x and the instruction scheduler.  A one-series look-ahead variant of the dense step
 // (MKF_LOOKAHEAD=1: d_{i+1} = P h_{i+1} - g_i (d_i.h_{i+1}) computed while 1/f_i is in
 // flight) is kept for reference; it costs 44 more fp64 instructions per step and measured
@@ -57,8 +57,11 @@ constexpr bool kLookAhead = MKF_LOOKAHEAD != 0;
 
 // time steps per tile: TT*M even (16-byte rows) and, where possible, TT*M = 2 (mod 4) so the
 // 64-bit LDS of a warp (row pitch TT*M doubles) is only 2-way bank conflicted
+#ifndef MKF_TT_ODD
+#define MKF_TT_ODD 6
+#endif
 __host__ __device__ constexpr int tile_steps(int M) {
-    return (M % 2 == 1) ? 6 : ((M % 4 == 2) ? 5 : 6);
+    return (M % 2 == 1) ? MKF_TT_ODD : ((M % 4 == 2) ? 5 : 6);
 }
 __host__ __device__ constexpr int const_count(int M, int K) { return (M + K) + M * K; }
 __host__ __device__ constexpr int warp_doubles(int M, int K) {
@@ -128,7 +131,8 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     // ---- per-model constants ---------------------------------------------------------
     double phi[N];
     double R[M];
-    constexpr bool GREG = (M * K <= 16) && (M + K <= 8);   // loadings in registers when they fit
+    constexpr bool GREG = (M * K <= 16) && (M + K <= 8);   // q and the loadings in registers when they fit
+    double qreg[GREG ? M + K : 1];
     double Greg[GREG ? M * K + 1 : 1];
     const int64_t bb = active ? b : b0;  // idle lanes of a ragged last warp shadow its first model
     {
@@ -161,6 +165,10 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) cst[i * 32] = q[i];
+        if (GREG) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) qreg[GREG ? i : 0] = q[i];
+        }
 #pragma unroll
         for (int i = 0; i < M * K; ++i) cst[(N + i) * 32] = G[i];
         if (GREG) {
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         }
         __syncwarp();
     }
-#define MKF_QQ(i) lds_f64(cst + (i) * 32)
+#define MKF_QQ(i) (GREG ? qreg[GREG ? (i) : 0] : lds_f64(cst + (i) * 32))
 #define MKF_GG(i) (GREG ? Greg[GREG ? (i) : 0] : lds_f64(cst + (N + (i)) * 32))
 
     // ---- state: x0 = 0, P0 = I (kalmanfilter.py:747-750) ------------------------------

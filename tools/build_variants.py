@@ -1,0 +1,28 @@
+"""Build K1 variants into metran_b200/lib/variants/*.so (compile-time switches) for A/B probes."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from metran_b200 import build
+VARIANTS = {
+    "base": [],
+    "tt8": ["-DMKF_TT_ODD=8"],
+    "tt10": ["-DMKF_TT_ODD=10"],
+    "tt4": ["-DMKF_TT_ODD=4"],
+    "kahan": ["-DMKF_KAHAN_CLASSIC=1"],
+    "qreg": ["-DMKF_Q_IN_REGS=1"],
+    "qreg_kahan": ["-DMKF_Q_IN_REGS=1", "-DMKF_KAHAN_CLASSIC=1"],
+}
+out = os.path.join(ROOT, "metran_b200", "lib", "variants")
+os.makedirs(out, exist_ok=True)
+srcs = ["api.cu", "filter_dfm.cu", "filter_dfm_k0.cu", "filter_dfm_k1.cu", "filter_dfm_k2.cu", "filter_dfm_k3.cu"]
+for name, flags in VARIANTS.items():
+    objs = []
+    for s in srcs:
+        o = os.path.join(out, "%s_%s.o" % (name, s[:-3]))
+        cmd = [build.nvcc_path()] + build.NVCC_FLAGS + ["-DMKF_DFM_ONLY_M5"] + flags + ["-c", os.path.join(build.CSRC, s), "-o", o]
+        subprocess.check_call(cmd, stderr=subprocess.DEVNULL)
+        objs.append(o)
+    # stubs for K = 0..2 launchers are not needed: link only what the probe uses (K = 3)
+    lib = os.path.join(out, "lib_%s.so" % name)
+    subprocess.check_call([build.nvcc_path(), "-shared", "-o", lib] + objs + ["-cudart", "static"])
+    print(name, os.path.getsize(lib))
