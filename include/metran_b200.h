@@ -13,6 +13,7 @@
  *                             metran/metran.py:605-622, metran/solver.py:42-63)
  *   mkf_dfm_loglik       <- same, for Metran-shaped models   metran/metran.py:265-416
  *                            (A, Q diagonal; H = [I | loadings]; quirk Q13 of SURVEY.md)
+ *   mkf_dfm_filter_history <- seqkalmanfilter for Metran-shaped batches (thread per model)
  *   mkf_dfm_loglik_alpha <- Metran._get_matrices + the above metran/metran.py:246-416, 605-622
  *                            (parameter vector alpha -> phi, q on the device)
  *   mkf_smoother         <- kalmansmoother(...)              metran/kalmanfilter.py:403-476
@@ -124,6 +125,23 @@ int mkf_dfm_loglik(int64_t B, int64_t T, int32_t m, int32_t k,
                    const double *r, int64_t r_stride,
                    int32_t warmup,
                    double *mle, int64_t *nobs, int32_t *status, void *stream);
+
+/*
+ * mkf_filter_history for Metran-shaped models, one thread per model (same arithmetic as
+ * mkf_dfm_loglik): the warp transposes its 32 per-step records through shared memory so the
+ * history leaves in contiguous 256-byte pieces; bound by HBM writes (8 [2(n + n^2) + 2.5]
+ * bytes per time step and model).  Output layout and semantics as mkf_filter_history.
+ */
+int mkf_dfm_filter_history(int64_t B, int64_t T, int32_t m, int32_t k,
+                           const double *y, int64_t y_stride,
+                           const double *phi, int64_t phi_stride,
+                           const double *q, int64_t q_stride,
+                           const double *gamma, int64_t gamma_stride,
+                           const double *r, int64_t r_stride,
+                           int32_t warmup,
+                           double *sigma, double *detf, int32_t *cnt,
+                           double *fm, double *fc, double *pm, double *pc,
+                           double *mle, int64_t *nobs, int32_t *status, void *stream);
 
 /*
  * As mkf_dfm_loglik with the parameter -> matrix map of Metran fused in front:

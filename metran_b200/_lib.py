@@ -29,6 +29,8 @@ SIGNATURES = {
                           + [_ptr] * 3 + [_ptr]),
     "mkf_dfm_loglik": (ctypes.c_int,
                        [_i64, _i64, _i32, _i32] + [_ptr, _i64] * 5 + [_i32] + [_ptr] * 3 + [_ptr]),
+    "mkf_dfm_filter_history": (ctypes.c_int,
+                               [_i64, _i64, _i32, _i32] + [_ptr, _i64] * 5 + [_i32] + [_ptr] * 10 + [_ptr]),
     "mkf_dfm_loglik_alpha": (ctypes.c_int,
                              [_i64, _i64, _i32, _i32, _ptr, _i64, _ptr, _i64, _dbl, _ptr, _i64, _i32]
                              + [_ptr] * 3 + [_ptr]),

@@ -199,6 +199,34 @@ class KalmanEngine:
         _lib.check(self.lib, rc, "mkf_dfm_loglik")
         return mle, nobs, status
 
+    def dfm_filter_history(self, y, phi, q, gamma, r=None, warmup=1, covariances=True):
+        """filter_history for Metran-shaped models on the thread-per-model kernel
+        (mkf_dfm_filter_history): same result dict as ``filter_history``."""
+        y, phi, q, gamma, r = (self.tensor(v) for v in (y, phi, q, gamma, r))
+        B = self._batch((y, 2), (phi, 1), (q, 1), (gamma, 2), (r, 1))
+        T, m = int(y.shape[-2]), int(y.shape[-1])
+        n = int(phi.shape[-1])
+        k = n - m
+        if gamma.shape[-2:] != (m, k):
+            raise ValueError("gamma must be [.., m, k] with k = n - m")
+        out = dict(
+            sigma=self.empty(B, T), detf=self.empty(B, T), cnt=self.empty(B, T, dtype=torch.int32),
+            fm=self.empty(B, T, n), pm=self.empty(B, T, n),
+            fc=self.empty(B, T, n, n) if covariances else None,
+            pc=self.empty(B, T, n, n) if covariances else None,
+            mle=self.empty(B), nobs=self.empty(B, dtype=torch.int64),
+            status=self.empty(B, dtype=torch.int32))
+        rc = self.lib.mkf_dfm_filter_history(
+            B, T, m, k, _ptr(y), self._stride(y, 2), _ptr(phi), self._stride(phi, 1),
+            _ptr(q), self._stride(q, 1), _ptr(gamma), self._stride(gamma, 2),
+            _ptr(r), self._stride(r, 1), int(warmup),
+            _ptr(out["sigma"]), _ptr(out["detf"]), _ptr(out["cnt"]),
+            _ptr(out["fm"]), _ptr(out["fc"]), _ptr(out["pm"]), _ptr(out["pc"]),
+            _ptr(out["mle"]), _ptr(out["nobs"]), _ptr(out["status"]), self._stream())
+        _lib.check(self.lib, rc, "mkf_dfm_filter_history")
+        out["flags"] = _lib.FLAG_A_DIAGONAL | _lib.FLAG_Q_DIAGONAL
+        return out
+
     def dfm_loglik_alpha(self, y, alpha, gamma, dt=1.0, warmup=1, out=None):
         """As dfm_loglik with Metran's alpha -> (phi, q) map fused (metran.py:246-416)."""
         y, alpha, gamma = self.tensor(y), self.tensor(alpha), self.tensor(gamma)

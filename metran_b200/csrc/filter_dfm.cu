@@ -91,6 +91,24 @@ extern "C" int mkf_dfm_loglik_alpha(int64_t B, int64_t T, int32_t m, int32_t k, 
     return mkf_dfm::run(m, k, a, (cudaStream_t)stream);
 }
 
+extern "C" int mkf_dfm_filter_history(int64_t B, int64_t T, int32_t m, int32_t k, const double *y, int64_t y_stride,
+                                      const double *phi, int64_t phi_stride, const double *q, int64_t q_stride,
+                                      const double *gamma, int64_t gamma_stride, const double *r, int64_t r_stride,
+                                      int32_t warmup, double *sigma, double *detf, int32_t *cnt, double *fm,
+                                      double *fc, double *pm, double *pc, double *mle, int64_t *nobs,
+                                      int32_t *status, void *stream) {
+    if (!phi || !q || !mle) return MKF_ERR_BAD_ARG;
+    if (!(sigma || detf || cnt || fm || fc || pm || pc)) return MKF_ERR_BAD_ARG;
+    mkf_dfm::DfmArgs a{};
+    a.B = B; a.T = T; a.y = y; a.y_stride = y_stride;
+    a.phi = phi; a.phi_stride = phi_stride; a.q = q; a.q_stride = q_stride;
+    a.gamma = gamma; a.gamma_stride = gamma_stride; a.r = r; a.r_stride = r_stride;
+    a.alpha = nullptr; a.dt = 1.0; a.warmup = warmup;
+    a.mle = mle; a.nobs = nobs; a.status = status;
+    a.sigma = sigma; a.detf = detf; a.cnt = cnt; a.fm = fm; a.fc = fc; a.pm = pm; a.pc = pc;
+    return mkf_dfm::run(m, k, a, (cudaStream_t)stream);
+}
+
 extern "C" void mkf_limits(int32_t *n_max, int32_t *dfm_m_max, int32_t *dfm_k_max) {
     if (n_max) *n_max = 32;
     if (dfm_m_max) *dfm_m_max = mkf_dfm::kMaxM;

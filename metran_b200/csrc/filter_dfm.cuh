@@ -46,6 +46,10 @@ struct DfmArgs {
     double *mle;
     int64_t *nobs;
     int32_t *status;
+    // history mode (reference result contract, kalmanfilter.py:392-400); NULL pointers are skipped
+    double *sigma, *detf;
+    int32_t *cnt;
+    double *fm, *fc, *pm, *pc;
 };
 
 constexpr int kBlock = 32;  // one warp per CTA: CTAs spread evenly over the 592 SMSPs
@@ -67,8 +71,10 @@ __host__ __device__ constexpr int const_count(int M, int K) { return (M + K) + M
 __host__ __device__ constexpr int warp_doubles(int M, int K) {
     return kStages * 32 * tile_steps(M) * M + 32 * const_count(M, K);
 }
-__host__ __device__ constexpr size_t smem_bytes(int M, int K) {
-    return 128 + (size_t)(kBlock / 32) * (warp_doubles(M, K) * sizeof(double) + kStages * sizeof(uint64_t));
+__host__ __device__ constexpr int hist_doubles(int M, int K) { return ((M + K) + (M + K) * (M + K)) * 33; }
+__host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false) {
+    return 128 + (size_t)(kBlock / 32) * ((warp_doubles(M, K) + (hist ? hist_doubles(M, K) : 0)) * sizeof(double) +
+                                           kStages * sizeof(uint64_t));
 }
 
 __device__ __forceinline__ double lds_f64(const double *p) {
@@ -95,13 +101,13 @@ __host__ __device__ constexpr int sym(int r, int c) {
     return r <= c ? tri<N>(r, c) : tri<N>(c, r);
 }
 
-template <int M, int K, bool HASR>
+template <int M, int K, bool HASR, bool HIST>
 __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, const __grid_constant__ CUtensorMap ymap) {
     constexpr int N = M + K;
     constexpr int NT = N * (N + 1) / 2;
     constexpr int TT = tile_steps(M);
     constexpr int PITCH = TT * M;  // doubles per model row of a tile
-    constexpr int WARP_DOUBLES = warp_doubles(M, K);
+    constexpr int WARP_DOUBLES = warp_doubles(M, K) + (HIST ? hist_doubles(M, K) : 0);
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem_al =
         smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // TMA destinations: 128 B aligned
@@ -109,6 +115,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *ring = reinterpret_cast<double *>(smem_al) + (size_t)warp * WARP_DOUBLES;
     double *cst = ring + kStages * 32 * PITCH + lane;  // constant i of this lane: cst[i * 32]
+    double *hst = ring + warp_doubles(M, K);           // history staging [N + N*N][33] (HIST only)
     uint64_t *bars =
         reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_al) + (size_t)(kBlock / 32) * WARP_DOUBLES) +
         warp * kStages;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 #pragma unroll
         for (int i = 0; i < M * K; ++i) G[i] = gp[i];
 #pragma unroll
-        for (int i = 0; i < M; ++i) R[i] = HASR ? a.r[bb * a.r_stride + i] : 0.0;
+        for (int i = 0; i < M; ++i) R[i] = (HASR && a.r) ? a.r[bb * a.r_stride + i] : 0.0;
         if (a.alpha) {
             // metran.py:262-263, 310-322
             const double *al = a.alpha + bb * a.alpha_stride;
@@ -188,6 +195,45 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     for (int r = 0; r < N; ++r)
 #pragma unroll
         for (int c = r; c < N; ++c) P[tri<N>(r, c)] = (r == c) ? 1.0 : 0.0;
+
+    // History mode: the warp transposes its 32 per-thread records through shared memory
+    // ([element][lane], pitch 33: conflict-free writes, 2-way reads) so that every store
+    // instruction covers one contiguous 256-byte piece of a model's [n] / [n][n] block.
+    auto emit = [&](double *gmean, double *gcov, int64_t t) {
+        if (!HIST) return;
+#pragma unroll
+        for (int i = 0; i < N; ++i) hst[i * 33 + lane] = x[i];
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) hst[(N + r * N + c) * 33 + lane] = P[sym<N>(r, c)];
+        __syncwarp();
+        const int rows = (int)min((int64_t)32, a.B - b0);
+        if (gcov) {
+            if (rows == 32) {   // full warp: unrolled so that several LDS/STG pairs are in flight
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    double *dst = gcov + ((b0 + rr) * a.T + t) * (N * N);
+#pragma unroll
+                    for (int e = lane; e < N * N; e += 32) dst[e] = hst[(N + e) * 33 + rr];
+                }
+            } else {
+                for (int rr = 0; rr < rows; ++rr) {
+                    double *dst = gcov + ((b0 + rr) * a.T + t) * (N * N);
+#pragma unroll
+                    for (int e = lane; e < N * N; e += 32) dst[e] = hst[(N + e) * 33 + rr];
+                }
+            }
+        }
+        if (gmean) {
+#pragma unroll
+            for (int idx = lane; idx < 32 * N; idx += 32) {
+                const int rr = idx / N, e = idx % N;
+                if (rr < rows) gmean[((b0 + rr) * a.T + t) * N + e] = hst[e * 33 + rr];
+            }
+        }
+        __syncwarp();
+    };
 
     KahanSum sum_sigma;
     double fprod = 1.0;  // running product of innovation variances, mantissa in [1,2)
@@ -264,6 +310,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                     double v = (phi[r] * P[tri<N>(r, c)]) * phi[c];
                     P[tri<N>(r, c)] = (r == c) ? v + MKF_QQ(r) : v;
                 }
+            emit(a.pm, a.pc, t0 + tt);
             // fold the PREVIOUS step's sigma / product of f into the running sums here, in
             // the shadow of this step's arithmetic (branch-free: neutral elements when the
             // previous step does not count)
@@ -425,6 +472,13 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                     }
                 }
             }
+            emit(a.fm, a.fc, t0 + tt);
+            if (HIST && active) {
+                const int64_t o = b * a.T + t0 + tt;
+                if (a.sigma) a.sigma[o] = sigma;
+                if (a.detf) a.detf[o] = (cnt > 0) ? log(stepprod) : 0.0;
+                if (a.cnt) a.cnt[o] = cnt;
+            }
             // quirk Q4 (kalmanfilter.py:563-566): the first `warmup` OBSERVED steps are
             // dropped from the sums, nobs counts raw steps t >= warmup
             pend_on = (cnt > 0) && (nsig >= a.warmup);
@@ -456,7 +510,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
                       int box_rows, int box_elems);
 
-template <int M, int K, bool HASR>
+template <int M, int K, bool HASR, bool HIST>
 int launch_r(const DfmArgs &a0, cudaStream_t stream) {
     DfmArgs a = a0;
     alignas(64) CUtensorMap map;
@@ -468,8 +522,8 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
                                    shared_y ? 1 : 32, TT * M);
         if (rc != MKF_OK) a.use_tma = 0;  // cp.async staging instead
     }
-    auto kern = dfm_loglik_kernel<M, K, HASR>;
-    const size_t smem = smem_bytes(M, K);
+    auto kern = dfm_loglik_kernel<M, K, HASR, HIST>;
+    const size_t smem = smem_bytes(M, K, HIST);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         mkf_host::set_cuda_error(e);
@@ -482,7 +536,9 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
 
 template <int M, int K>
 int launch(const DfmArgs &a, cudaStream_t stream) {
-    return a.r ? launch_r<M, K, true>(a, stream) : launch_r<M, K, false>(a, stream);
+    const bool hist = a.sigma || a.detf || a.cnt || a.fm || a.fc || a.pm || a.pc;
+    if (hist) return launch_r<M, K, true, true>(a, stream);
+    return a.r ? launch_r<M, K, true, false>(a, stream) : launch_r<M, K, false, false>(a, stream);
 }
 
 // one translation unit per K instantiates M = 1..8 (keeps nvcc wall time parallel)

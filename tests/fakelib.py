@@ -134,6 +134,26 @@ class FakeLib:
         return self._dfm(B, T, m, k, y, ys, lambda b, G: _model(phi, b, ps, (n,)),
                          lambda b, G: _model(q, b, qs, (n,)), gamma, gs, r, rs, warmup, mle, nobs, status)
 
+    def mkf_dfm_filter_history(self, B, T, m, k, y, ys, phi, ps, q, qs, gamma, gs, r, rs, warmup,
+                               sigma, detf, cnt, fm, fc, pm, pc, mle, nobs, status, stream):
+        self.calls.append(("mkf_dfm_filter_history", B, T, m, k))
+        if m > 8 or k > 3:
+            return 2
+        n = m + k
+        # expand to the generic layout in host memory, then reuse _filter
+        A = np.zeros((B, n, n)); Q = np.zeros((B, n, n)); H = np.zeros((B, m, n)); R = np.zeros((B, m))
+        for b in range(B):
+            A[b] = np.diag(_model(phi, b, ps, (n,)))
+            Q[b] = np.diag(_model(q, b, qs, (n,)))
+            H[b, :, :m] = np.eye(m)
+            if k:
+                H[b, :, m:] = _model(gamma, b, gs, (m, k))
+            if _addr(r):
+                R[b] = _model(r, b, rs, (m,))
+        P = lambda a_: a_.ctypes.data
+        return self._filter(B, T, n, m, y, ys, P(A), n * n, P(Q), n * n, P(H), m * n, P(R), m, None, 0, None, 0,
+                            warmup, 3, sigma, detf, cnt, fm, fc, pm, pc, mle, nobs, status)
+
     def mkf_dfm_loglik_alpha(self, B, T, m, k, y, ys, alpha, als, dt, gamma, gs, warmup, mle, nobs, status, stream):
         self.calls.append(("mkf_dfm_loglik_alpha", B, T, m, k))
         n = m + k

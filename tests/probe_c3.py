@@ -24,3 +24,21 @@ for (B, T, n, m) in ((256, 1000, 32, 64), (4096, 500, 8, 5), (16384, 500, 8, 5),
     hb = B * T * 8 * (m + 2 * (n + n * n) + 3); sb = B * T * 8 * 3 * (n + n * n)
     print(f"n={n} m={m} B={B} T={T}: loglik {t1:.2f} ms ({B*T/t1*1e3:.2e}/s) | history {t2:.2f} ms ({B*T/t2*1e3:.2e}/s, {hb/t2/1e6:.0f} GB/s) | smoother {t3:.2f} ms ({B*T/t3*1e3:.2e}/s, {sb/t3/1e6:.0f} GB/s)", flush=True)
     del out
+# thread-per-model history kernel for Metran-shaped models
+for (B, T) in ((16384, 500), (23680, 400), (28416, 400), (37888, 300)):
+    m, k = 5, 3; n = 8
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    y = torch.randn(B, T, m, dtype=torch.float64, device=dev, generator=g)
+    phi = torch.rand(B, n, dtype=torch.float64, device=dev, generator=g) * 0.2 + 0.75
+    q = 1 - phi**2
+    G = (torch.rand(B, m, k, dtype=torch.float64, device=dev, generator=g) * 0.6 + 0.3) / np.sqrt(k)
+    t4 = timeit(lambda: eng.dfm_filter_history(y, phi, q, G))
+    hb = B * T * 8 * (m + 2 * (n + n * n) + 2.5)
+    print(f"DFM thread-per-model history n=8 m=5 B={B} T={T}: {t4:.2f} ms ({B*T/t4*1e3:.2e}/s, {hb/t4/1e6:.0f} GB/s)", flush=True)
+# pure-write and copy bandwidth references (torch kernels)
+buf = torch.empty(2 * 1024**3 // 8 * 4, dtype=torch.float64, device=dev)   # 8 GB
+tz = timeit(lambda: buf.zero_())
+print(f"torch zero_ 8 GB: {tz:.2f} ms -> {buf.numel()*8/tz/1e6:.0f} GB/s write", flush=True)
+src = torch.empty_like(buf)
+tc = timeit(lambda: buf.copy_(src))
+print(f"torch copy_ 8 GB: {tc:.2f} ms -> {2*buf.numel()*8/tc/1e6:.0f} GB/s read+write", flush=True)

@@ -187,3 +187,50 @@ def test_nonpositive_f_is_flagged(eng):
     mle, nobs, status = eng.filter_loglik(y, A, Q, H, R)
     assert int(status[0]) & 1
     assert not np.isfinite(float(mle[0]))
+
+
+@pytest.mark.parametrize("tag", CASE_TAGS)
+def test_dfm_history_golden(eng, cases, tag):
+    """Thread-per-model history kernel (mkf_dfm_filter_history) against the reference's arrays."""
+    c = cases[tag]
+    parts = _dfm_parts(c)
+    if parts is None or not _default_init(c):
+        pytest.skip("not Metran-shaped")
+    phi, q, G = parts
+    m, k = G.shape
+    if not eng.dfm_supported(m, k):
+        pytest.skip("outside the compiled DFM kernels")
+    out = eng.dfm_filter_history(c["y"][None], phi[None], q[None], G[None], r=c["R"][None])
+    cnt = _np(out["cnt"])[0]
+    assert np.array_equal(cnt, c["ocnt"])
+    seen = cnt > 0
+    np.testing.assert_allclose(_np(out["sigma"])[0][seen], c["sigmas"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(_np(out["detf"])[0][seen], c["detfs"], rtol=0, atol=1e-11)
+    for key in ("fm", "fc", "pm", "pc"):
+        np.testing.assert_allclose(_np(out[key])[0], c[key], rtol=0, atol=STATE_TOL, err_msg=key)
+    assert abs(float(out["mle"][0]) - float(c["mle"])) <= MLE_TOL
+    sm, sc, _ = eng.smoother(out["fm"], out["fc"], out["pm"], out["pc"], c["A"])
+    np.testing.assert_allclose(_np(sm)[0], c["sm"], rtol=0, atol=1e-8)
+
+
+def test_dfm_history_batch_matches_generic_kernel(eng):
+    """Ragged batch (B = 203): thread-per-model history == warp-group history to rounding."""
+    rng = np.random.default_rng(21)
+    B, T, m, k = 203, 97, 5, 3
+    y, alpha, phi, q, G = _random_dfm_batch(rng, B, T, m, k, 0.25)
+    n = m + k
+    A = np.zeros((B, n, n)); Q = np.zeros((B, n, n)); H = np.zeros((B, m, n))
+    idx = np.arange(n)
+    A[:, idx, idx] = phi; Q[:, idx, idx] = q
+    H[:, np.arange(m), np.arange(m)] = 1.0; H[:, :, m:] = G
+    ref = eng.filter_history(y, A, Q, H, np.zeros((B, m)), flags=3)
+    out = eng.dfm_filter_history(y, phi, q, G)
+    assert torch.equal(out["cnt"], ref["cnt"]) and torch.equal(out["nobs"], ref["nobs"])
+    for key in ("sigma", "detf", "fm", "fc", "pm", "pc", "mle"):
+        np.testing.assert_allclose(_np(out[key]), _np(ref[key]), rtol=0, atol=1e-9, err_msg=key)
+    # and against the oracle for a few models
+    for b in (0, 101, 202):
+        obs, oi, oc = ko.pack_observations(y[b])
+        _, _, _, fm, fc, pm, pc = ko.seqkalmanfilter(obs, A[b], Q[b], H[b], np.zeros(m), oi, oc, np.zeros(n), np.eye(n))
+        np.testing.assert_allclose(_np(out["fc"])[b], fc, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(_np(out["pm"])[b], pm, rtol=0, atol=1e-9)

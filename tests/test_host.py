@@ -205,3 +205,16 @@ def test_shard_bounds_cover_batch():
             spans = [shard_bounds(total, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_dfm_filter_history_argument_packing(eng, cases):
+    """mkf_dfm_filter_history: compact (phi, q, gamma) layout -> reference result contract."""
+    c = cases["dfm_n8_m5_miss30"]
+    m = c["H"].shape[0]
+    out = eng.dfm_filter_history(c["y"][None], np.diag(c["A"])[None], np.diag(c["Q"])[None], c["H"][:, m:][None])
+    cnt = out["cnt"][0].numpy()
+    assert np.array_equal(cnt, c["ocnt"])
+    np.testing.assert_allclose(out["sigma"][0].numpy()[cnt > 0], c["sigmas"], atol=1e-12)
+    for key in ("fm", "fc", "pm", "pc"):
+        np.testing.assert_allclose(out[key][0].numpy(), c[key], atol=1e-12)
+    assert abs(float(out["mle"][0]) - float(c["mle"])) < 1e-10
