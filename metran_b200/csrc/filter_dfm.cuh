@@ -64,16 +64,21 @@ constexpr bool kLookAhead = MKF_LOOKAHEAD != 0;
 #ifndef MKF_TT_ODD
 #define MKF_TT_ODD 6
 #endif
-__host__ __device__ constexpr int tile_steps(int M) {
-    return (M % 2 == 1) ? MKF_TT_ODD : ((M % 4 == 2) ? 5 : 6);
+// history mode is bound by its stores and wants many resident warps: short tiles there
+__host__ __device__ constexpr int tile_steps(int M, bool hist = false) {
+    return hist ? ((M % 2 == 1) ? 2 : 1) : ((M % 2 == 1) ? MKF_TT_ODD : ((M % 4 == 2) ? 5 : 6));
 }
-__host__ __device__ constexpr int const_count(int M, int K) { return (M + K) + M * K; }
-__host__ __device__ constexpr int warp_doubles(int M, int K) {
-    return kStages * 32 * tile_steps(M) * M + 32 * const_count(M, K);
+// q and the loadings live in registers when they fit (then no shared-memory copy is needed)
+__host__ __device__ constexpr bool consts_in_regs(int M, int K) { return (M * K <= 16) && (M + K <= 8); }
+__host__ __device__ constexpr int const_count(int M, int K) {
+    return consts_in_regs(M, K) ? 0 : (M + K) + M * K;
+}
+__host__ __device__ constexpr int warp_doubles(int M, int K, bool hist = false) {
+    return kStages * 32 * tile_steps(M, hist) * M + 32 * const_count(M, K);
 }
 __host__ __device__ constexpr int hist_doubles(int M, int K) { return ((M + K) + (M + K) * (M + K)) * 33; }
 __host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false) {
-    return 128 + (size_t)(kBlock / 32) * ((warp_doubles(M, K) + (hist ? hist_doubles(M, K) : 0)) * sizeof(double) +
+    return 128 + (size_t)(kBlock / 32) * ((warp_doubles(M, K, hist) + (hist ? hist_doubles(M, K) : 0)) * sizeof(double) +
                                            kStages * sizeof(uint64_t));
 }
 
@@ -105,9 +110,9 @@ template <int M, int K, bool HASR, bool HIST>
 __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, const __grid_constant__ CUtensorMap ymap) {
     constexpr int N = M + K;
     constexpr int NT = N * (N + 1) / 2;
-    constexpr int TT = tile_steps(M);
+    constexpr int TT = tile_steps(M, HIST);
     constexpr int PITCH = TT * M;  // doubles per model row of a tile
-    constexpr int WARP_DOUBLES = warp_doubles(M, K) + (HIST ? hist_doubles(M, K) : 0);
+    constexpr int WARP_DOUBLES = warp_doubles(M, K, HIST) + (HIST ? hist_doubles(M, K) : 0);
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem_al =
         smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // TMA destinations: 128 B aligned
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *ring = reinterpret_cast<double *>(smem_al) + (size_t)warp * WARP_DOUBLES;
     double *cst = ring + kStages * 32 * PITCH + lane;  // constant i of this lane: cst[i * 32]
-    double *hst = ring + warp_doubles(M, K);           // history staging [N + N*N][33] (HIST only)
+    double *hst = ring + warp_doubles(M, K, HIST);     // history staging [N + N*N][33] (HIST only)
     uint64_t *bars =
         reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_al) + (size_t)(kBlock / 32) * WARP_DOUBLES) +
         warp * kStages;
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     // ---- per-model constants ---------------------------------------------------------
     double phi[N];
     double R[M];
-    constexpr bool GREG = (M * K <= 16) && (M + K <= 8);   // q and the loadings in registers when they fit
+    constexpr bool GREG = consts_in_regs(M, K);   // q and the loadings in registers when they fit
     double qreg[GREG ? M + K : 1];
     double Greg[GREG ? M * K + 1 : 1];
     const int64_t bb = active ? b : b0;  // idle lanes of a ragged last warp shadow its first model
@@ -170,14 +175,15 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 q[i] = a.q[bb * a.q_stride + i];
             }
         }
-#pragma unroll
-        for (int i = 0; i < N; ++i) cst[i * 32] = q[i];
         if (GREG) {
 #pragma unroll
             for (int i = 0; i < N; ++i) qreg[GREG ? i : 0] = q[i];
-        }
+        } else {
 #pragma unroll
-        for (int i = 0; i < M * K; ++i) cst[(N + i) * 32] = G[i];
+            for (int i = 0; i < N; ++i) cst[i * 32] = q[i];
+#pragma unroll
+            for (int i = 0; i < M * K; ++i) cst[(N + i) * 32] = G[i];
+        }
         if (GREG) {
 #pragma unroll
             for (int i = 0; i < M * K; ++i) Greg[GREG ? i : 0] = G[i];
@@ -515,7 +521,7 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
     DfmArgs a = a0;
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    constexpr int TT = tile_steps(M);
+    constexpr int TT = tile_steps(M, HIST);
     if (a.use_tma) {
         const bool shared_y = a.y_stride == 0;
         int rc = make_y_tensor_map(&map, a.y, shared_y ? 1 : a.B, a.T * M, shared_y ? a.T * M : a.y_stride,
