@@ -7,7 +7,7 @@
 //   v = y_j - h.x          (butterfly shuffle reduction)
 //   d_r = P[r,:].h         (row in registers, h broadcast from shared memory)
 //   f = R_j + h.d          (butterfly)
-//   g_r = d_r / f ; P[r,:] -= d_r g^T ; x_r += g_r v
+//   g_r = d_r (1/f) ; P[r,:] -= d_r g^T ; x_r += g_r v     (one branch-free reciprocal per series)
 // so the only cross-lane traffic is two reductions and one n-vector broadcast.
 // Observations are NaN-coded and streamed model-major through a cp.async double-buffered
 // shared-memory ring; missing series are skipped with a ballot (the C0 data set has
@@ -45,7 +45,6 @@ __host__ __device__ inline int round_up2(int v) { return (v + 1) & ~1; }
 template <int NP, bool HIST>
 __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a) {
     extern __shared__ __align__(16) double smem[];
-    constexpr int GPW = 32 / NP;  // model groups per warp
     const int n = a.n, m = a.m;
     const int group_in_block = threadIdx.x / NP;
     const int r = threadIdx.x % NP;
@@ -54,7 +53,6 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
     const int gshift = group_in_warp * NP;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x / NP) + group_in_block;
     if (b >= a.B) return;  // whole groups leave together; masks below are per group
-    (void)GPW;
 
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
     const bool diagQ = a.flags & MKF_FLAG_Q_DIAGONAL;
@@ -173,7 +171,7 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
 
             // ---- sequential update over observed series (kalmanfilter.py:335-382) ----
             double sigma = 0.0, fman = 1.0;
-            int fexp = 0, bad_step = 0;
+            int fexp = 0;
             int cnt = 0;
             for (int j0 = 0; j0 < m; j0 += NP) {
                 const int jj = j0 + r;
@@ -238,7 +236,6 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
                     if (f_is_bad(f)) status |= MKF_STATUS_NONPOSITIVE_F;
                 }
             }
-            (void)bad_step;
             const double detf = (cnt > 0) ? log(fman) + (double)fexp * kLn2 : 0.0;
             if (cnt > 0) {
                 if (nsig >= a.warmup) {
