@@ -305,6 +305,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if local_rank == 0:                      # no-op when metran_b200/lib/libmetran_b200.so is current
+        from metran_b200 import build as _build
+
+        _build.build()
+    if world > 1:
+        dist.barrier()
     from metran_b200.batched import KalmanEngine
 
     eng = KalmanEngine(device=dev)
