@@ -21,4 +21,8 @@ def __getattr__(name):
         from . import dfm
 
         return getattr(dfm, name)
+    if name in ("fit_dfm_batch", "BatchFitResult"):
+        from . import fit
+
+        return getattr(fit, name)
     raise AttributeError(name)

@@ -218,3 +218,24 @@ def test_dfm_filter_history_argument_packing(eng, cases):
     for key in ("fm", "fc", "pm", "pc"):
         np.testing.assert_allclose(out[key][0].numpy(), c[key], atol=1e-12)
     assert abs(float(out["mle"][0]) - float(c["mle"])) < 1e-10
+
+
+def test_batched_fit_reaches_the_reference_optimum(eng, nbmodel):
+    """fit_dfm_batch: several starts of the notebook model all reach the reference's optimum
+    (examples/dynamic_factor_model.ipynb data; -2logL at the optimum from the live reference)."""
+    from metran_b200.fit import fit_dfm_batch
+
+    g = nbmodel
+    y = g["y"][:600]
+    B = 3
+    starts = np.array([[10.0, 10.0, 10.0], [4.0, 30.0, 15.0], [25.0, 6.0, 40.0]])
+    res = fit_dfm_batch(eng, np.broadcast_to(y, (B,) + y.shape).copy(),
+                        np.broadcast_to(g["factors"], (B,) + g["factors"].shape).copy(), alpha0=starts)
+    assert res.converged.all()
+    # reference optimum on the same truncated data through the single-model path
+    from metran_b200.dfm import DynamicFactorModel
+
+    mdl = DynamicFactorModel(y, g["factors"], engine=eng)
+    mdl.solve()
+    assert np.all(np.abs(res.obj - mdl.parameters["obj_func"]) < 1e-4)
+    np.testing.assert_allclose(res.alpha, np.tile(mdl.parameters["optimal"], (B, 1)), rtol=5e-3)
