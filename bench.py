@@ -480,7 +480,7 @@ def main():
                  "peak_source": "measured live by mkf_probe_fp64 (DFMA microbenchmark, same process)",
                  "algorithmic_flops_per_timestep_model": flops_per_step(n, m),
                  "ncu_pipe_fp64_cycles_active_pct": pipe_pct,
-                 "note": "frac > 1 because the kernel exploits the model structure: 592 fp64 instructions per "
+                 "note": "frac > 1 because the kernel exploits the model structure: 538 fp64 instructions per "
                          "unit instead of 1117.5 FMAs; ncu_pipe_* is the measured pipe occupancy of the last "
                          "committed capture (profiles/)"},
     }
