@@ -20,6 +20,8 @@
 //
 // mkf_project replaces the per-time-step Python loop of SPKalmanFilter.simulate
 // (metran/kalmanfilter.py:596-602).
+#include <type_traits>
+
 #include "mkf_common.cuh"
 
 namespace {
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
 
     // For NP <= 8 the inputs of step t-1 are fetched into registers while step t computes
     // (global-load latency off the critical path); at NP >= 16 the extra registers spill.
-    constexpr bool PREFETCH = NP <= 8;
+    constexpr bool PREFETCH = NP <= 16;
     constexpr int NPF = PREFETCH ? NP : 1;
     double nL[NPF], nF[NPF], nxp = 0.0, nxf = 0.0;
     auto fetch = [&](int64_t t, double *Lr, double *Fr, double &xp_, double &xf_) {
@@ -186,17 +188,22 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
                 for (int i = 0; i < NP; ++i) z[i] = fma(sA[i * LD + k], pk, z[i]);
             }
         }
+        // The factor is read through a volatile pointer in the (fully unrolled) substitutions:
+        // ptxas otherwise hoists hundreds of shared-memory loads ahead of their use and spills
+        // (4.5 KB of local memory per thread at NP = 32).
+        typedef typename std::conditional<(NP >= 16), const volatile double, const double>::type LRead;
+        LRead *vL = sL;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {  // forward substitution, column oriented
             z[k] *= sinv[k];
 #pragma unroll
-            for (int i = k + 1; i < NP; ++i) z[i] = fma(-sL[i * LD + k], z[k], z[i]);
+            for (int i = k + 1; i < NP; ++i) z[i] = fma(-vL[i * LD + k], z[k], z[i]);
         }
 #pragma unroll
         for (int k = NP - 1; k >= 0; --k) {  // backward substitution with L^T
             z[k] *= sinv[k];
 #pragma unroll
-            for (int i = 0; i < k; ++i) z[i] = fma(-sL[k * LD + i], z[k], z[i]);
+            for (int i = 0; i < k; ++i) z[i] = fma(-vL[k * LD + i], z[k], z[i]);
         }
         // rows/cols >= n: P_f row is zero -> z = 0 there.
 

@@ -10,7 +10,7 @@ def timeit(fn, reps=3):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return min(ts)
-for (B, T, n, m) in ((256, 1000, 32, 64), (4096, 100, 32, 64), (16384, 500, 8, 5)):
+for (B, T, n, m) in ((256, 1000, 32, 64), (4096, 100, 32, 64), (2048, 200, 16, 12), (16384, 500, 8, 5)):
     g = torch.Generator(device=dev); g.manual_seed(2)
     y = torch.randn(B, T, m, dtype=torch.float64, device=dev, generator=g)
     phi = torch.rand(B, n, dtype=torch.float64, device=dev, generator=g) * 0.2 + 0.75
