@@ -441,6 +441,41 @@ def main():
                       "note": "observations resident on the device (they do not change between objective "
                               "evaluations of a fit), parameters up / -2logL down every step"}
 
+    # ---- the small BASELINE.json configurations, same kernels, device-timed (rank 0, informative) ----
+    other = None
+    if rank == 0 and args.config == "metric":
+        other = {}
+
+        def dev_time(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            best = None
+            for _ in range(reps):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                fn()
+                a1.record()
+                torch.cuda.synchronize()
+                ms = a0.elapsed_time(a1)
+                best = ms if best is None else min(best, ms)
+            return best
+
+        B1, T1 = CONFIGS["c1"][0], CONFIGS["c1"][1]
+        ms1 = dev_time(lambda: eng.dfm_loglik_alpha(y[:B1, :T1].contiguous(), alpha[:B1], gamma[:B1]))
+        other["c1_1024_models_T2000"] = {"ms": ms1, "value": B1 * T1 / (ms1 * 1e-3), "unit": UNIT,
+                                         "note": "32 warps on 592 SMSPs: bound by the latency of one model's recursion"}
+        try:
+            g21 = np.load(os.path.join(ROOT, "tests", "golden", "b21b0214.npz"))
+            y21 = torch.as_tensor(g21["y"], device=dev)
+            f21 = torch.as_tensor(g21["factors"], device=dev)
+            draws = torch.as_tensor(np.random.default_rng(5).uniform(1.0, 100.0, (8192, y21.shape[1] + f21.shape[1])), device=dev)
+            ms2 = dev_time(lambda: eng.dfm_loglik_alpha(y21, draws, f21))
+            other["c2_8192_draws_of_B21B0214_T%d" % y21.shape[0]] = {
+                "ms": ms2, "value": 8192 * y21.shape[0] / (ms2 * 1e-3), "unit": UNIT,
+                "note": "the reference's example data (shared observations, 94.5 % empty days)"}
+        except Exception as exc:                      # fixture missing: informative only
+            other["c2"] = {"skipped": str(exc)[:80]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -501,6 +536,7 @@ def main():
         "config": workload_config(args, cfg, world),
         "clocks": clocks, "e2e": e2e, "e2e_solver_step": e2e_solver, "gpu_launches": 2 * args.steps,
         "roofline": roofline, "cpu_baseline": cpu,
+        "other_configs": other,
         "check": {"pooled_minus2logL": pooled_value, "models_with_status": bad},
     }
     print(json.dumps(line), flush=True)
