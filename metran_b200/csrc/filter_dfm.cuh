@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <string.h>
 
+#include "dfm_collapsed.cuh"
 #include "mkf_common.cuh"
 
 namespace mkf_dfm {
@@ -73,13 +74,28 @@ __host__ __device__ constexpr bool consts_in_regs(int M, int K) { return (M * K 
 __host__ __device__ constexpr int const_count(int M, int K) {
     return consts_in_regs(M, K) ? 0 : (M + K) + M * K;
 }
-__host__ __device__ constexpr int warp_doubles(int M, int K, bool hist = false) {
-    return kStages * 32 * tile_steps(M, hist) * M + 32 * const_count(M, K);
+// Collapsed (factor-only) dense step, dfm_collapsed.cuh: its constants D, S0, QG sit in shared
+// memory next to q / Gamma.  Enabled for the shapes whose CTA still fits 8 to an SM
+// (2 warps per SMSP at <= 255 registers): (228 KB - 8 x 1 KB reserved) / 8.
+#ifndef MKF_COLLAPSE
+#define MKF_COLLAPSE 1
+#endif
+__host__ __device__ constexpr int plain_warp_doubles(int M, int K) {
+    return kStages * 32 * tile_steps(M, false) * M + 32 * const_count(M, K);
+}
+__host__ __device__ constexpr bool collapse_shape(int M, int K) {
+    return MKF_COLLAPSE != 0 && K >= 1 &&
+           128 + (plain_warp_doubles(M, K) + 32 * collapsed_const_count(M, K)) * 8 + kStages * 8 <= 28160;
+}
+__host__ __device__ constexpr int warp_doubles(int M, int K, bool hist = false, bool collapse = false) {
+    return kStages * 32 * tile_steps(M, hist) * M + 32 * const_count(M, K) +
+           ((collapse && collapse_shape(M, K)) ? 32 * collapsed_const_count(M, K) : 0);
 }
 __host__ __device__ constexpr int hist_doubles(int M, int K) { return ((M + K) + (M + K) * (M + K)) * 33; }
-__host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false) {
-    return 128 + (size_t)(kBlock / 32) * ((warp_doubles(M, K, hist) + (hist ? hist_doubles(M, K) : 0)) * sizeof(double) +
-                                           kStages * sizeof(uint64_t));
+__host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false, bool collapse = false) {
+    return 128 + (size_t)(kBlock / 32) *
+                     ((warp_doubles(M, K, hist, collapse) + (hist ? hist_doubles(M, K) : 0)) * sizeof(double) +
+                      kStages * sizeof(uint64_t));
 }
 
 __device__ __forceinline__ double lds_f64(const double *p) {
@@ -96,23 +112,15 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
-// index of (r, c), r <= c, in the packed upper triangle of an N x N matrix
-template <int N>
-__host__ __device__ constexpr int tri(int r, int c) {
-    return r * N - (r * (r - 1)) / 2 + (c - r);
-}
-template <int N>
-__host__ __device__ constexpr int sym(int r, int c) {
-    return r <= c ? tri<N>(r, c) : tri<N>(c, r);
-}
-
 template <int M, int K, bool HASR, bool HIST>
 __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, const __grid_constant__ CUtensorMap ymap) {
     constexpr int N = M + K;
     constexpr int NT = N * (N + 1) / 2;
     constexpr int TT = tile_steps(M, HIST);
     constexpr int PITCH = TT * M;  // doubles per model row of a tile
-    constexpr int WARP_DOUBLES = warp_doubles(M, K, HIST) + (HIST ? hist_doubles(M, K) : 0);
+    // factor-only dense steps need R = 0 and no history output
+    constexpr bool COLLAPSE = !HASR && !HIST && collapse_shape(M, K);
+    constexpr int WARP_DOUBLES = warp_doubles(M, K, HIST, COLLAPSE) + (HIST ? hist_doubles(M, K) : 0);
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem_al =
         smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // TMA destinations: 128 B aligned
@@ -120,7 +128,8 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *ring = reinterpret_cast<double *>(smem_al) + (size_t)warp * WARP_DOUBLES;
     double *cst = ring + kStages * 32 * PITCH + lane;  // constant i of this lane: cst[i * 32]
-    double *hst = ring + warp_doubles(M, K, HIST);     // history staging [N + N*N][33] (HIST only)
+    double *ccs = cst + 32 * const_count(M, K);        // collapsed-step constant i: ccs[i * 32]
+    double *hst = ring + warp_doubles(M, K, HIST, COLLAPSE);  // history staging [N + N*N][33] (HIST only)
     uint64_t *bars =
         reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_al) + (size_t)(kBlock / 32) * WARP_DOUBLES) +
         warp * kStages;
@@ -188,6 +197,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 #pragma unroll
             for (int i = 0; i < M * K; ++i) Greg[GREG ? i : 0] = G[i];
         }
+        if constexpr (COLLAPSE) collapsed_consts<M, K>(phi, q, G, [&](int i, double v) { ccs[i * 32] = v; });
         __syncwarp();
     }
 #define MKF_QQ(i) (GREG ? qreg[GREG ? (i) : 0] : lds_f64(cst + (i) * 32))
@@ -247,6 +257,10 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     int nobs = 0;
     int nsig = 0;
     bool bad = false;
+    bool collapsed = false;  // state held as (c, C, y_prev): previous step fully observed in all lanes
+    double yp[M];            // previous step's observations (collapsed mode)
+#pragma unroll
+    for (int i = 0; i < M; ++i) yp[i] = 0.0;
     bool pend_on = false;  // previous step's contribution, folded one step later
     double pend_sigma = 0.0, pend_prod = 1.0;
 
@@ -306,17 +320,15 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 #pragma unroll
             for (int i = 0; i < M; ++i) yn[i] = ys[tn * M + i];
 
-            // ---- predict: x = phi x ; P = phi P phi + Q (kalmanfilter.py:318-331) -----
+            bool all_obs = true, any_obs = false;
 #pragma unroll
-            for (int i = 0; i < N; ++i) x[i] *= phi[i];
-#pragma unroll
-            for (int r = 0; r < N; ++r)
-#pragma unroll
-                for (int c = r; c < N; ++c) {
-                    double v = (phi[r] * P[tri<N>(r, c)]) * phi[c];
-                    P[tri<N>(r, c)] = (r == c) ? v + MKF_QQ(r) : v;
-                }
-            emit(a.pm, a.pc, t0 + tt);
+            for (int i = 0; i < M; ++i) {
+                const bool o = is_observed(yv[i]);
+                all_obs = all_obs && o;
+                any_obs = any_obs || o;
+            }
+            const bool warp_any = __any_sync(0xffffffffu, any_obs);
+            const bool warp_all = __all_sync(0xffffffffu, all_obs);
             // fold the PREVIOUS step's sigma / product of f into the running sums here, in
             // the shadow of this step's arithmetic (branch-free: neutral elements when the
             // previous step does not count)
@@ -328,27 +340,53 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 fexp += ex;
                 fprod = __hiloint2double(hi - (ex << 20), __double2loint(fprod));
             }
-
-            // ---- sequential scalar updates (kalmanfilter.py:341-378) -------------------
             double sigma = 0.0, stepprod = 1.0;
             int cnt = 0;
-            bool all_obs = true, any_obs = false;
+            bool factor_only = false;
+            if constexpr (COLLAPSE) {
+                if (collapsed && warp_all) {
+                    // this and the previous step fully observed in every lane: factor-only step
+                    // (dfm_collapsed.cuh), predict included
+                    factor_only = true;
+                    cnt = M;
+                    double qc[K];
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const bool o = is_observed(yv[i]);
-                all_obs = all_obs && o;
-                any_obs = any_obs || o;
+                    for (int j = 0; j < K; ++j) qc[j] = MKF_QQ(M + j);
+                    collapsed_step<M, K>(x, P, phi, qc, yp, yv, [&](int i) { return lds_f64(ccs + i * 32); },
+                                         sigma, stepprod, bad);
+                }
             }
-            if (!__any_sync(0xffffffffu, any_obs)) {
+            if (!factor_only) {
+            if constexpr (COLLAPSE) {
+                if (collapsed) {
+                    collapsed_expand<M, K>(x, P, yp, [&](int i) { return MKF_GG(i); });
+                    collapsed = false;
+                }
+            }
+            // ---- predict: x = phi x ; P = phi P phi + Q (kalmanfilter.py:318-331) -----
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] *= phi[i];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = r; c < N; ++c) {
+                    double v = (phi[r] * P[tri<N>(r, c)]) * phi[c];
+                    P[tri<N>(r, c)] = (r == c) ? v + MKF_QQ(r) : v;
+                }
+            emit(a.pm, a.pc, t0 + tt);
+
+            // ---- sequential scalar updates (kalmanfilter.py:341-378) -------------------
+            if (!warp_any) {
                 // nobody in the warp observes anything at this step (irregular sampling on a
                 // daily grid: 94.5 % of the steps of the reference's example data): predict only
-            } else if (__all_sync(0xffffffffu, all_obs)) {
+            } else if (warp_all) {
                 // Dense step, straight-line code with one-series look-ahead: while the
                 // reciprocal of f_i is in flight, e = P h_{i+1} and s = h_{i+1}.d_i are
                 // computed from the NOT yet updated P; afterwards
                 //   d_{i+1} = (P - g d^T) h_{i+1} = e - g s
                 // which is the same vector the reference gets from the updated P.
                 cnt = M;
+                if (COLLAPSE) collapsed = true;
                 if (kLookAhead) {
                 double d[N], e[N], gc[K + 1], gn[K + 1];
 #pragma unroll
@@ -478,6 +516,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                     }
                 }
             }
+            }  // ordinary (full-state) step
             emit(a.fm, a.fc, t0 + tt);
             if (HIST && active) {
                 const int64_t o = b * a.T + t0 + tt;
@@ -493,7 +532,10 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             nsig += (cnt > 0) ? 1 : 0;
             nobs += (t0 + tt >= a.warmup) ? cnt : 0;
 #pragma unroll
-            for (int i = 0; i < M; ++i) yv[i] = yn[i];
+            for (int i = 0; i < M; ++i) {
+                if (COLLAPSE) yp[i] = yv[i];
+                yv[i] = yn[i];
+            }
         }
     }
     if (!tma) cp_async_wait<0>();
@@ -529,7 +571,7 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
         if (rc != MKF_OK) a.use_tma = 0;  // cp.async staging instead
     }
     auto kern = dfm_loglik_kernel<M, K, HASR, HIST>;
-    const size_t smem = smem_bytes(M, K, HIST);
+    const size_t smem = smem_bytes(M, K, HIST, !HASR && !HIST);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         mkf_host::set_cuda_error(e);

@@ -170,6 +170,47 @@ def test_dfm_random_batch_vs_oracle(eng, m, k, T, miss):
     assert np.array_equal(_np(nobs_g), wobs)
 
 
+@pytest.mark.parametrize("m,k,T", [(5, 3, 420), (5, 3, 36), (4, 2, 301), (6, 2, 150), (2, 1, 97), (5, 1, 64),
+                                   (8, 3, 80), (6, 3, 77)])
+def test_dfm_collapse_transitions_vs_oracle(eng, m, k, T):
+    """Runs of fully observed steps use the factor-only step (dfm_collapsed.cuh) when EVERY lane
+    of the warp is dense; this batch makes warps collapse, expand and re-collapse:
+    warp 0 dense throughout, warp 1 with gaps shared by all its lanes (rows fully missing or one
+    series missing), warp 2 dense except single lanes with private gaps, warp 3 ragged."""
+    rng = np.random.default_rng(77 + 13 * m + k + T)
+    B = 32 * 3 + 9
+    y, alpha, phi, q, G = _random_dfm_batch(rng, B, T, m, k, 0.0)
+    rows = rng.random(T) < 0.15
+    y[32:64, rows] = np.nan                                   # whole-step gaps, warp-wide
+    y[32:64, (rng.random(T) < 0.1) & ~rows, 0] = np.nan       # one series missing, warp-wide
+    y[40, T // 2, m - 1] = -1e10                              # the reference's drop sentinel
+    for lane in (64, 70, 95):
+        y[lane, rng.random(T) < 0.2, rng.integers(0, m)] = np.nan
+    y[96:, : T // 3] = np.nan                                 # late start in the ragged warp
+    y[100, -1] = np.nan
+    n = m + k
+    A = np.zeros((B, n, n)); Q = np.zeros((B, n, n)); H = np.zeros((B, m, n))
+    idx = np.arange(n)
+    A[:, idx, idx] = phi
+    Q[:, idx, idx] = q
+    H[:, np.arange(m), np.arange(m)] = 1.0
+    H[:, :, m:] = G
+    R = np.zeros((B, m))
+    for warmup in (1, 4):
+        want, wobs = ko.filter_loglik_batch(y, A, Q, H, R, warmup=warmup)
+        mle, nobs, status = eng.dfm_loglik(y, phi, q, G, warmup=warmup)
+        np.testing.assert_allclose(_np(mle), want, rtol=1e-12, atol=MLE_TOL)
+        assert np.array_equal(_np(nobs), wobs)
+        assert not _np(status).any()
+        mle_a, _, _ = eng.dfm_loglik_alpha(y, alpha, G, warmup=warmup)
+        np.testing.assert_allclose(_np(mle_a), want, rtol=1e-12, atol=MLE_TOL)
+    # R != 0 must take the ordinary path (H P != 0 after an update) and still agree
+    Rn = np.full((B, m), 0.05)
+    want, _ = ko.filter_loglik_batch(y, A, Q, H, Rn)
+    mle_r, _, _ = eng.dfm_loglik(y, phi, q, G, r=Rn)
+    np.testing.assert_allclose(_np(mle_r), want, rtol=1e-12, atol=MLE_TOL)
+
+
 def test_reduce_sum_deterministic(eng):
     v = torch.randn(100003, dtype=torch.float64, device=eng.device) * 1e3
     a = float(eng.reduce_sum(v)[0])
