@@ -257,14 +257,12 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     int nobs = 0;
     int nsig = 0;
     bool bad = false;
-    bool collapsed = false;  // state held as (c, C, y_prev): previous step fully observed in all lanes
-    double yp[M];            // previous step's observations (collapsed mode)
-#pragma unroll
-    for (int i = 0; i < M; ++i) yp[i] = 0.0;
     bool pend_on = false;  // previous step's contribution, folded one step later
     double pend_sigma = 0.0, pend_prod = 1.0;
 
     const int64_t T = a.T;
+    // (a box must start 16-byte aligned in global memory or the TMA engine faults with "illegal
+    // instruction": TT*M is even for every M, see tile_steps)
     const int64_t ntiles = (T + TT - 1) / TT;
     const double *yb = a.y + bb * a.y_stride;
     // shared y: the tile holds ONE row that every lane reads (broadcast)
@@ -277,7 +275,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             return;
         }
         const int s = (int)(tile % kStages);
-        const int64_t t0 = tile * TT;
+        const int64_t tb = tile * TT;   // first step of the box
         double *stage = ring + (size_t)s * 32 * PITCH;
         if (tma) {
             // WAR across proxies: the lanes' earlier LDS of this stage vs. the async write
@@ -285,20 +283,28 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_expect_tx(&bars[s], shared_y ? (unsigned)(PITCH * 8) : kTileBytes);
-                tma_load_2d(stage, &ymap, (int)(t0 * M), shared_y ? 0 : (int)b0, &bars[s]);
+                tma_load_2d(stage, &ymap, (int)(tb * M), shared_y ? 0 : (int)b0, &bars[s]);
             }
         } else {
-            const int nel = (int)min((int64_t)TT, T - t0) * M;
+            const int nel = (int)min((int64_t)TT, T - tb) * M;
             double *dst = stage + (size_t)lane * PITCH;
-            const double *src = yb + t0 * M;
+            const double *src = yb + tb * M;
             if (active)
                 for (int e = 0; e < nel; ++e) cp_async8(dst + e, src + e);
             cp_async_commit();
         }
     };
 
-    issue_tile(0);
-    for (int64_t tile = 0; tile < ntiles; ++tile) {
+    // ---- time loop, flattened over (tile, step) ----------------------------------------
+    // Two loops advance through the same sequence of steps with next_step(): the full-state
+    // loop and, for COLLAPSE builds, the factor-only loop (dfm_collapsed.cuh) that takes over
+    // after a step every lane observed completely.  Inside the factor-only loop P_ss, P_sc and
+    // x_s are dead, which leaves their registers to the instruction scheduler.
+    int64_t tile = 0, t0 = 0;
+    int tt = 0, steps = 0;
+    const double *ys = myrow;
+    double yv[M], yn[M];
+    auto open_tile = [&]() {   // start fetching tile + 1, wait for `tile`
         issue_tile(tile + 1);
         const int s = (int)(tile % kStages);
         if (tma) {
@@ -306,63 +312,79 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         } else {
             cp_async_wait<kStages - 1>();
         }
-        const double *ys = myrow + (size_t)s * 32 * PITCH;
-        const int64_t t0 = tile * TT;
-        const int steps = (int)min((int64_t)TT, T - t0);
+        ys = myrow + (size_t)s * 32 * PITCH;
+        t0 = tile * TT;
+        steps = (int)min((int64_t)TT, T - t0);
+        tt = 0;
+    };
+    // prefetch the next step's observations of this tile (LDS latency off the path)
+    auto prefetch_next = [&]() {
+        const int tn = (tt + 1 < steps) ? tt + 1 : tt;
+#pragma unroll
+        for (int i = 0; i < M; ++i) yn[i] = ys[tn * M + i];
+    };
+    auto advance = [&]() -> bool {
+        if (++tt < steps) return true;
+        if (++tile >= ntiles) return false;
+        open_tile();
+        return true;
+    };
+    auto next_step = [&]() -> bool {   // full-state loop: yv = observations of the step to do
+        const bool same_tile = tt + 1 < steps;
+        const bool m = advance();
+#pragma unroll
+        for (int i = 0; i < M; ++i) yv[i] = same_tile ? yn[i] : ys[i];
+        return m;
+    };
+    // fold the PREVIOUS step's sigma / product of f into the running sums, in the shadow of
+    // the current step's arithmetic (branch-free: neutral elements when it does not count)
+    auto fold = [&]() {
+        sum_sigma.add(pend_on ? pend_sigma : 0.0);
+        fprod *= pend_on ? pend_prod : 1.0;
+        const int hi = __double2hiint(fprod);
+        const int ex = ((hi >> 20) & 0x7ff) - 1023;
+        fexp += ex;
+        fprod = __hiloint2double(hi - (ex << 20), __double2loint(fprod));
+    };
+    auto account = [&](int cnt, double sigma, double stepprod) {
+        if (HIST && active) {
+            const int64_t o = b * a.T + t0 + tt;
+            if (a.sigma) a.sigma[o] = sigma;
+            if (a.detf) a.detf[o] = (cnt > 0) ? log(stepprod) : 0.0;
+            if (a.cnt) a.cnt[o] = cnt;
+        }
+        // quirk Q4 (kalmanfilter.py:563-566): the first `warmup` OBSERVED steps are
+        // dropped from the sums, nobs counts raw steps t >= warmup
+        pend_on = (cnt > 0) && (nsig >= a.warmup);
+        pend_sigma = sigma;
+        pend_prod = stepprod;
+        nsig += (cnt > 0) ? 1 : 0;
+        nobs += (t0 + tt >= a.warmup) ? cnt : 0;
+    };
 
-        double yv[M], yn[M];
+    issue_tile(0);
+    bool more = ntiles > 0;
+    if (more) {
+        open_tile();
 #pragma unroll
         for (int i = 0; i < M; ++i) yv[i] = ys[i];
-
-        for (int tt = 0; tt < steps; ++tt) {
-            // prefetch the next step's observations of this tile (LDS latency off the path)
-            const int tn = (tt + 1 < steps) ? tt + 1 : tt;
-#pragma unroll
-            for (int i = 0; i < M; ++i) yn[i] = ys[tn * M + i];
-
-            bool all_obs = true, any_obs = false;
+    }
+    while (more) {
+        bool warp_all;
+        {
+            prefetch_next();
+            unsigned all_obs = 1u, any_obs = 0u;   // bitwise: no short-circuit branches
 #pragma unroll
             for (int i = 0; i < M; ++i) {
-                const bool o = is_observed(yv[i]);
-                all_obs = all_obs && o;
-                any_obs = any_obs || o;
+                const unsigned o = is_observed(yv[i]) ? 1u : 0u;
+                all_obs &= o;
+                any_obs |= o;
             }
-            const bool warp_any = __any_sync(0xffffffffu, any_obs);
-            const bool warp_all = __all_sync(0xffffffffu, all_obs);
-            // fold the PREVIOUS step's sigma / product of f into the running sums here, in
-            // the shadow of this step's arithmetic (branch-free: neutral elements when the
-            // previous step does not count)
-            sum_sigma.add(pend_on ? pend_sigma : 0.0);
-            fprod *= pend_on ? pend_prod : 1.0;
-            {
-                const int hi = __double2hiint(fprod);
-                const int ex = ((hi >> 20) & 0x7ff) - 1023;
-                fexp += ex;
-                fprod = __hiloint2double(hi - (ex << 20), __double2loint(fprod));
-            }
+            const bool warp_any = __any_sync(0xffffffffu, any_obs != 0u);
+            warp_all = __all_sync(0xffffffffu, all_obs != 0u);
+            fold();
             double sigma = 0.0, stepprod = 1.0;
             int cnt = 0;
-            bool factor_only = false;
-            if constexpr (COLLAPSE) {
-                if (collapsed && warp_all) {
-                    // this and the previous step fully observed in every lane: factor-only step
-                    // (dfm_collapsed.cuh), predict included
-                    factor_only = true;
-                    cnt = M;
-                    double qc[K];
-#pragma unroll
-                    for (int j = 0; j < K; ++j) qc[j] = MKF_QQ(M + j);
-                    collapsed_step<M, K>(x, P, phi, qc, yp, yv, [&](int i) { return lds_f64(ccs + i * 32); },
-                                         sigma, stepprod, bad);
-                }
-            }
-            if (!factor_only) {
-            if constexpr (COLLAPSE) {
-                if (collapsed) {
-                    collapsed_expand<M, K>(x, P, yp, [&](int i) { return MKF_GG(i); });
-                    collapsed = false;
-                }
-            }
             // ---- predict: x = phi x ; P = phi P phi + Q (kalmanfilter.py:318-331) -----
 #pragma unroll
             for (int i = 0; i < N; ++i) x[i] *= phi[i];
@@ -386,7 +408,6 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 //   d_{i+1} = (P - g d^T) h_{i+1} = e - g s
                 // which is the same vector the reference gets from the updated P.
                 cnt = M;
-                if (COLLAPSE) collapsed = true;
                 if (kLookAhead) {
                 double d[N], e[N], gc[K + 1], gn[K + 1];
 #pragma unroll
@@ -516,25 +537,53 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                     }
                 }
             }
-            }  // ordinary (full-state) step
             emit(a.fm, a.fc, t0 + tt);
-            if (HIST && active) {
-                const int64_t o = b * a.T + t0 + tt;
-                if (a.sigma) a.sigma[o] = sigma;
-                if (a.detf) a.detf[o] = (cnt > 0) ? log(stepprod) : 0.0;
-                if (a.cnt) a.cnt[o] = cnt;
-            }
-            // quirk Q4 (kalmanfilter.py:563-566): the first `warmup` OBSERVED steps are
-            // dropped from the sums, nobs counts raw steps t >= warmup
-            pend_on = (cnt > 0) && (nsig >= a.warmup);
-            pend_sigma = sigma;
-            pend_prod = stepprod;
-            nsig += (cnt > 0) ? 1 : 0;
-            nobs += (t0 + tt >= a.warmup) ? cnt : 0;
+            account(cnt, sigma, stepprod);
+        }
+        if (!(COLLAPSE && warp_all)) more = next_step();
+        if constexpr (COLLAPSE) {
+            // the step just done was observed completely in every lane: (c, C, y_prev) carry the
+            // whole posterior from here until a step with a missing value turns up.  In this loop
+            // yv is NOT rotated: it keeps the observations of the last step of the previous tile
+            // (needed as y(t-1) at tt = 0, when that tile's stage is already being refilled).
+            if (warp_all) {
+                more = advance();
+                while (more) {
+                    // y(t) and y(t-1) straight from the ring; across a tile boundary y(t-1) is the
+                    // register copy in yv (its stage is being refilled)
+                    const double *yr = ys + (tt > 0 ? tt - 1 : 0) * M;
+                    double yc[M], yq[M];
+                    unsigned all_obs = 1u;
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                if (COLLAPSE) yp[i] = yv[i];
-                yv[i] = yn[i];
+                    for (int i = 0; i < M; ++i) {
+                        yc[i] = ys[tt * M + i];
+                        all_obs &= is_observed(yc[i]) ? 1u : 0u;
+                    }
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        const double prev = yr[i];
+                        yq[i] = (tt > 0) ? prev : yv[i];
+                    }
+                    if (!__all_sync(0xffffffffu, all_obs != 0u)) {
+                        collapsed_expand<M, K>(x, P, yq, [&](int i) { return MKF_GG(i); });
+#pragma unroll
+                        for (int i = 0; i < M; ++i) yv[i] = yc[i];
+                        break;   // the full-state loop handles this step
+                    }
+                    fold();
+                    double sigma = 0.0, stepprod = 1.0;
+                    double qc[K];
+#pragma unroll
+                    for (int j = 0; j < K; ++j) qc[j] = MKF_QQ(M + j);
+                    collapsed_step<M, K>(x, P, phi, qc, yq, yc, [&](int i) { return lds_f64(ccs + i * 32); },
+                                         sigma, stepprod, bad);
+                    account(M, sigma, stepprod);
+                    if (tt + 1 == steps) {
+#pragma unroll
+                        for (int i = 0; i < M; ++i) yv[i] = yc[i];
+                    }
+                    more = advance();
+                }
             }
         }
     }

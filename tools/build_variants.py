@@ -5,12 +5,9 @@ sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
     "base": [],
-    "tt8": ["-DMKF_TT_ODD=8"],
-    "tt10": ["-DMKF_TT_ODD=10"],
-    "tt4": ["-DMKF_TT_ODD=4"],
-    "kahan": ["-DMKF_KAHAN_CLASSIC=1"],
-    "qreg": ["-DMKF_Q_IN_REGS=1"],
-    "qreg_kahan": ["-DMKF_Q_IN_REGS=1", "-DMKF_KAHAN_CLASSIC=1"],
+    "neg": ["-DMKF_TILE0_SPECIAL=0"],
+    "ov2": ["-DMKF_OV=2"],
+    "nocollapse": ["-DMKF_COLLAPSE=0"],
 }
 out = os.path.join(ROOT, "metran_b200", "lib", "variants")
 os.makedirs(out, exist_ok=True)

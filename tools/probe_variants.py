@@ -13,7 +13,7 @@ G = (torch.rand(B, m, k, dtype=torch.float64, device=dev, generator=g) * 0.6 + 0
 mle = torch.empty(B, dtype=torch.float64, device=dev); nobs = torch.empty(B, dtype=torch.int64, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev)
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 ref = None
-for path in sorted(glob.glob(os.path.join(ROOT, "metran_b200", "lib", "variants", "lib_*.so"))):
+for path in (sys.argv[1:] or sorted(glob.glob(os.path.join(ROOT, "metran_b200", "lib", "variants", "lib_*.so")))):
     L = ctypes.CDLL(path)
     res, args = _lib.SIGNATURES["mkf_dfm_loglik_alpha"]
     L.mkf_dfm_loglik_alpha.restype = res; L.mkf_dfm_loglik_alpha.argtypes = args
