@@ -27,10 +27,6 @@
 
 #include "mkf_common.cuh"
 
-#ifndef MKF_CS_EARLY
-#define MKF_CS_EARLY 0
-#endif
-
 namespace mkf_dfm {
 
 // index of (r, c), r <= c, in the packed upper triangle of an N x N matrix
@@ -46,20 +42,6 @@ __host__ __device__ constexpr int sym(int r, int c) {
 __host__ __device__ __forceinline__ double cs_rcp(double f) {
 #ifdef __CUDA_ARCH__
     return mkf::rcp_nr(f);
-#else
-    return 1.0 / f;
-#endif
-}
-// same value; on the device the seed is a volatile asm, which keeps its place among the
-// (volatile) shared-memory loads of the constants
-__host__ __device__ __forceinline__ double cs_rcp_pinned(double f) {
-#ifdef __CUDA_ARCH__
-    double y;
-    asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(f));
-    double e = fma(-f, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-f, y, 1.0);
-    return fma(y, e, y);
 #else
     return 1.0 / f;
 #endif
@@ -110,52 +92,6 @@ __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, co
     double D[M * K];
 #pragma unroll
     for (int i = 0; i < M * K; ++i) D[i] = ld(i);
-#if MKF_CS_EARLY
-    // order chosen so that the first pivot's reciprocal is in flight as early as possible:
-    // row 0 of W = D C, then S00, then everything else
-    double W[M * K];
-    double S[MT];
-    double Tm[K * M];
-    double v[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-#pragma unroll
-        for (int l = 0; l < K; ++l) {
-            double s = D[i * K] * P[sym<N>(M, M + l)];
-#pragma unroll
-            for (int j = 1; j < K; ++j) s = fma(D[i * K + j], P[sym<N>(M + j, M + l)], s);
-            W[i * K + l] = s;
-        }
-        if (i == 0) {
-            double s = ld(M * K + tri<M>(0, 0));
-#pragma unroll
-            for (int j = 0; j < K; ++j) s = fma(W[j], D[j], s);
-            S[tri<M>(0, 0)] = s;
-        }
-    }
-    double rf = cs_rcp_pinned(S[tri<M>(0, 0)]);
-#pragma unroll
-    for (int i = 0; i < M; ++i)
-#pragma unroll
-        for (int l = i; l < M; ++l) {
-            if (i == 0 && l == 0) continue;
-            double s = ld(M * K + tri<M>(i, l));
-#pragma unroll
-            for (int j = 0; j < K; ++j) s = fma(W[i * K + j], D[l * K + j], s);
-            S[tri<M>(i, l)] = s;
-        }
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-#pragma unroll
-        for (int i = 0; i < M; ++i) Tm[j * M + i] = fma(-phi[M + j], W[i * K + j], ld(M * K + MT + j * M + i));
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-        double s = fma(-phi[i], yp[i], yv[i]);
-#pragma unroll
-        for (int j = 0; j < K; ++j) s = fma(D[i * K + j], x[M + j], s);
-        v[i] = s;
-    }
-#else
     // innovations before any update of this step
     double v[M];
 #pragma unroll
@@ -193,7 +129,6 @@ __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, co
             for (int j = 0; j < K; ++j) s = fma(W[i * K + j], D[l * K + j], s);
             S[tri<M>(i, l)] = s;
         }
-#endif
     // predict the factor block
 #pragma unroll
     for (int j = 0; j < K; ++j) x[M + j] *= phi[M + j];
@@ -204,42 +139,7 @@ __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, co
             const double t = (phi[M + j] * P[tri<N>(M + j, M + l)]) * phi[M + l];
             P[tri<N>(M + j, M + l)] = (j == l) ? t + qc[j] : t;
         }
-    // pivot by pivot = series by series.  The reciprocal of pivot i+1 is started as soon as its
-    // value is known (one multiplier and one FMA into pivot i's elimination), so that its
-    // MUFU + Newton chain runs under the rest of pivot i's updates.
-#if MKF_CS_EARLY
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-        const double f = S[tri<M>(i, i)];
-        const double rfi = rf;
-        double mlt_next = 0.0;
-        if (i + 1 < M) {
-            mlt_next = S[tri<M>(i, i + 1)] * rfi;
-            S[tri<M>(i + 1, i + 1)] = fma(-mlt_next, S[tri<M>(i, i + 1)], S[tri<M>(i + 1, i + 1)]);
-            rf = cs_rcp(S[tri<M>(i + 1, i + 1)]);
-        }
-        bad = bad || cs_bad(f);
-        stepprod *= f;
-        sigma = fma(v[i] * v[i], rfi, sigma);
-#pragma unroll
-        for (int l = i + 1; l < M; ++l) {
-            const double mlt = (l == i + 1) ? mlt_next : S[tri<M>(i, l)] * rfi;
-            v[l] = fma(-mlt, v[i], v[l]);
-#pragma unroll
-            for (int l2 = l; l2 < M; ++l2)
-                if (!(l == i + 1 && l2 == i + 1)) S[tri<M>(l, l2)] = fma(-mlt, S[tri<M>(i, l2)], S[tri<M>(l, l2)]);
-#pragma unroll
-            for (int j = 0; j < K; ++j) Tm[j * M + l] = fma(-mlt, Tm[j * M + i], Tm[j * M + l]);
-        }
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const double g = Tm[j * M + i] * rfi;
-            x[M + j] = fma(g, v[i], x[M + j]);
-#pragma unroll
-            for (int l = j; l < K; ++l) P[tri<N>(M + j, M + l)] = fma(-g, Tm[l * M + i], P[tri<N>(M + j, M + l)]);
-        }
-    }
-#else
+    // pivot by pivot = series by series
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         const double f = S[tri<M>(i, i)];
@@ -264,7 +164,6 @@ __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, co
             for (int l = j; l < K; ++l) P[tri<N>(M + j, M + l)] = fma(-g, Tm[l * M + i], P[tri<N>(M + j, M + l)]);
         }
     }
-#endif
 }
 
 // Rebuild the full posterior (x, P) of the last fully observed step from (c, C, y_prev).

@@ -5,9 +5,8 @@ sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
     "base": [],
-    "neg": ["-DMKF_TILE0_SPECIAL=0"],
-    "ov2": ["-DMKF_OV=2"],
     "nocollapse": ["-DMKF_COLLAPSE=0"],
+    "tt4": ["-DMKF_TT_ODD=4"],
 }
 out = os.path.join(ROOT, "metran_b200", "lib", "variants")
 os.makedirs(out, exist_ok=True)
