@@ -39,6 +39,12 @@ __host__ __device__ constexpr int sym(int r, int c) {
     return r <= c ? tri<N>(r, c) : tri<N>(c, r);
 }
 
+// index of the multiplier (i, l), i < l, among the M(M-1)/2 strictly-upper pairs
+template <int M>
+__host__ __device__ constexpr int frozen_pair(int i, int l) {
+    return i * M - (i * (i + 1)) / 2 + (l - i - 1);
+}
+
 __host__ __device__ __forceinline__ double cs_rcp(double f) {
 #ifdef __CUDA_ARCH__
     return mkf::rcp_nr(f);
@@ -83,10 +89,13 @@ __host__ __device__ __forceinline__ void collapsed_consts(const double *phi, con
 // One fully observed step from the collapsed posterior of the previous (fully observed) step.
 // In/out: x[M..N) = c, P[cc block] = C (packed upper triangle of the N x N matrix).
 // The other entries of x and P are neither read nor written.
-template <int M, int K, class Load>
-__host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, const double *phi, const double *qc,
-                                                        const double *yp, const double *yv, Load ld, double &sigma,
-                                                        double &stepprod, bool &bad) {
+// With CAP the reciprocal pivots, the elimination multipliers and the gains of this step are
+// handed to cap(slot, value) (slots relative to constant M*K, layout of collapsed_frozen_step).
+template <int M, int K, bool CAP, class Load, class Cap>
+__host__ __device__ __forceinline__ void collapsed_step_impl(double *x, double *P, const double *phi,
+                                                             const double *qc, const double *yp, const double *yv,
+                                                             Load ld, Cap cap, double &sigma, double &stepprod,
+                                                             bool &bad) {
     constexpr int N = M + K;
     constexpr int MT = M * (M + 1) / 2;
     double D[M * K];
@@ -147,9 +156,11 @@ __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, co
         bad = bad || cs_bad(f);
         stepprod *= f;
         sigma = fma(v[i] * v[i], rf, sigma);
+        if (CAP) cap(i, rf);
 #pragma unroll
         for (int l = i + 1; l < M; ++l) {
             const double mlt = S[tri<M>(i, l)] * rf;
+            if (CAP) cap(M + frozen_pair<M>(i, l), mlt);
             v[l] = fma(-mlt, v[i], v[l]);
 #pragma unroll
             for (int l2 = l; l2 < M; ++l2) S[tri<M>(l, l2)] = fma(-mlt, S[tri<M>(i, l2)], S[tri<M>(l, l2)]);
@@ -159,11 +170,67 @@ __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, co
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const double g = Tm[j * M + i] * rf;
+            if (CAP) cap(MT + j * M + i, g);
             x[M + j] = fma(g, v[i], x[M + j]);
 #pragma unroll
             for (int l = j; l < K; ++l) P[tri<N>(M + j, M + l)] = fma(-g, Tm[l * M + i], P[tri<N>(M + j, M + l)]);
         }
     }
+}
+
+template <int M, int K, class Load>
+__host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, const double *phi, const double *qc,
+                                                        const double *yp, const double *yv, Load ld, double &sigma,
+                                                        double &stepprod, bool &bad) {
+    collapsed_step_impl<M, K, false>(x, P, phi, qc, yp, yv, ld, [](int, double) {}, sigma, stepprod, bad);
+}
+
+// Steady state.  For constant parameters the factor covariance C of consecutive fully observed
+// steps converges (Riccati iteration); once it has stopped changing, S, its LDL^T factors and
+// the gains are constants and a step is only
+//     v = y - phi_s*y_prev + D c;  c = phi_c c;  per series i: sigma += v_i^2/f_i,
+//     v_l -= m_il v_i (l > i),  c_j += g_ji v_i
+// i.e. exactly the operations of collapsed_step that involve the data, in the same order, with
+// 1/f_i, m_il, g_ji captured from the last full step (slots M*K.. of the constant block, over S0
+// and QG, which the frozen step does not need): M + M(M-1)/2 + K*M = M(M+1)/2 + K*M values.
+template <int M, int K, class Load>
+__host__ __device__ __forceinline__ void collapsed_frozen_step(double *x, const double *phi, const double *yp,
+                                                               const double *yv, Load ld, double &sigma) {
+    constexpr int MT = M * (M + 1) / 2;
+    double v[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double s = fma(-phi[i], yp[i], yv[i]);
+#pragma unroll
+        for (int j = 0; j < K; ++j) s = fma(ld(i * K + j), x[M + j], s);
+        v[i] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) x[M + j] *= phi[M + j];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        sigma = fma(v[i] * v[i], ld(M * K + i), sigma);
+#pragma unroll
+        for (int l = i + 1; l < M; ++l) v[l] = fma(-ld(M * K + M + frozen_pair<M>(i, l)), v[i], v[l]);
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[M + j] = fma(ld(M * K + MT + j * M + i), v[i], x[M + j]);
+    }
+}
+
+// Convergence monitor of the steady-state switch: one number per model that moves whenever an
+// entry of C moves (weights 1, sqrt(2)-ish ... chosen without simple ratios).
+template <int M, int K>
+__host__ __device__ __forceinline__ double collapsed_checksum(const double *P) {
+    constexpr int N = M + K;
+    constexpr double w[6] = {1.0, 0.7071067811865476, 0.5773502691896258, 1.618033988749895, 0.36787944117144233,
+                             1.2599210498948732};
+    double s = 0.0;
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = j; l < K; ++l) s = fma(w[n++ % 6], P[tri<N>(M + j, M + l)], s);
+    return s;
 }
 
 // Rebuild the full posterior (x, P) of the last fully observed step from (c, C, y_prev).

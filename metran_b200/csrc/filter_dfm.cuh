@@ -98,6 +98,14 @@ __host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false,
                       kStages * sizeof(uint64_t));
 }
 
+#ifndef MKF_FREEZE
+#define MKF_FREEZE 1
+#endif
+constexpr bool kFreeze = MKF_FREEZE != 0;
+constexpr double kFreezeTol = 8.8817841970012523e-16;   // 2^-50
+__device__ __forceinline__ void sts_f64(double *p, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(smem_u32(p)), "d"(v) : "memory");
+}
 __device__ __forceinline__ double lds_f64(const double *p) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)));
@@ -547,6 +555,17 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             // yv is NOT rotated: it keeps the observations of the last step of the previous tile
             // (needed as y(t-1) at tt = 0, when that tile's stage is already being refilled).
             if (warp_all) {
+                // Steady state (dfm_collapsed.cuh).  Each lane watches its own C; when it has stopped
+                // changing the lane HOLDS it (every later step restarts from the held value), so
+                // that its results do not depend on when the rest of the warp converges.  Once all
+                // lanes hold, one more full step stores their (now constant) reciprocal pivots,
+                // multipliers and gains and the warp switches to the data-only step.
+                constexpr int KT = K * (K + 1) / 2;
+                bool frozen = false, capture_next = false, lane_holds = false;
+                double frozen_prod = 1.0;
+                double cchk = -1.0;   // weighted sum of the entries of C at the last check
+                int nconv = 0;        // consecutive checks without change
+                volatile double Chold[KT];   // local memory on purpose: read back once per step
                 more = advance();
                 while (more) {
                     // y(t) and y(t-1) straight from the ring; across a tile boundary y(t-1) is the
@@ -565,6 +584,16 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                         yq[i] = (tt > 0) ? prev : yv[i];
                     }
                     if (!__all_sync(0xffffffffu, all_obs != 0u)) {
+                        if (kFreeze && frozen) {
+                            // S0 and QG were overwritten by the frozen gains: put them back
+                            double qq[N], gg[M * K];
+#pragma unroll
+                            for (int i = 0; i < N; ++i) qq[i] = MKF_QQ(i);
+#pragma unroll
+                            for (int i = 0; i < M * K; ++i) gg[i] = MKF_GG(i);
+                            collapsed_consts<M, K>(phi, qq, gg, [&](int i, double v) { sts_f64(ccs + i * 32, v); });
+                            __syncwarp();
+                        }
                         collapsed_expand<M, K>(x, P, yq, [&](int i) { return MKF_GG(i); });
 #pragma unroll
                         for (int i = 0; i < M; ++i) yv[i] = yc[i];
@@ -572,11 +601,54 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                     }
                     fold();
                     double sigma = 0.0, stepprod = 1.0;
-                    double qc[K];
+                    if (kFreeze && frozen) {
+                        collapsed_frozen_step<M, K>(x, phi, yq, yc, [&](int i) { return lds_f64(ccs + i * 32); }, sigma);
+                        stepprod = frozen_prod;
+                    } else {
+                        double qc[K];
 #pragma unroll
-                    for (int j = 0; j < K; ++j) qc[j] = MKF_QQ(M + j);
-                    collapsed_step<M, K>(x, P, phi, qc, yq, yc, [&](int i) { return lds_f64(ccs + i * 32); },
-                                         sigma, stepprod, bad);
+                        for (int j = 0; j < K; ++j) qc[j] = MKF_QQ(M + j);
+                        // one code path: when capture_next is set (warp-uniform) the step also stores
+                        // its reciprocal pivots, multipliers and gains over S0 / QG (predicated stores)
+                        collapsed_step_impl<M, K, kFreeze>(
+                            x, P, phi, qc, yq, yc, [&](int i) { return lds_f64(ccs + i * 32); },
+                            [&](int i, double v) {
+                                if (capture_next) sts_f64(ccs + (M * K + i) * 32, v);
+                            },
+                            sigma, stepprod, bad);
+                        if (kFreeze) {
+                            if (lane_holds) {
+#pragma unroll
+                                for (int j = 0; j < K; ++j)
+#pragma unroll
+                                    for (int l = j; l < K; ++l) P[tri<N>(M + j, M + l)] = Chold[tri<K>(j, l)];
+                            }
+                            if (capture_next) {
+                                __syncwarp();
+                                frozen_prod = stepprod;
+                                frozen = true;
+                                capture_next = false;
+                            } else if (tt == 0) {
+                                // once per tile: a weighted sum of the entries of C (weights without
+                                // simple ratios, so that opposite drifts do not cancel) must not have
+                                // moved by more than 2^-50 of itself over two consecutive tiles
+                                if (!lane_holds) {
+                                    const double cs = collapsed_checksum<M, K>(P);
+                                    const bool same = fabs(cs - cchk) <= kFreezeTol * fabs(cs);
+                                    cchk = cs;
+                                    nconv = same ? nconv + 1 : 0;
+                                    if (nconv >= 2) {
+                                        lane_holds = true;
+#pragma unroll
+                                        for (int j = 0; j < K; ++j)
+#pragma unroll
+                                            for (int l = j; l < K; ++l) Chold[tri<K>(j, l)] = P[tri<N>(M + j, M + l)];
+                                    }
+                                }
+                                capture_next = __all_sync(0xffffffffu, lane_holds);
+                            }
+                        }
+                    }
                     account(M, sigma, stepprod);
                     if (tt + 1 == steps) {
 #pragma unroll

@@ -24,6 +24,13 @@ static double run(int64_t T, const double *y, const double *phi, const double *q
     for (int r = 0; r < N; ++r)
         for (int c = r; c < N; ++c) P[tri<N>(r, c)] = (r == c) ? 1.0 : 0.0;
     double yp[M] = {0};
+    constexpr int MT = M * (M + 1) / 2;
+    constexpr int kCheckEvery = 6;
+    const double kFreezeTol = ldexp(1.0, -50);
+    bool frozen = false, capture_next = false;
+    int since_check = 0;
+    double frozen_prod = 1.0, cap[MT + K * M + 1], cchk = -1.0, Chold[K * (K + 1) / 2 + 1];
+    int nconv = 0;
     bool collapsed = false, bad = false;
     long double sum_sigma = 0.0L, sum_det = 0.0L;
     int64_t nobs = 0, nsig = 0;
@@ -39,12 +46,48 @@ static double run(int64_t T, const double *y, const double *phi, const double *q
         double sigma = 0.0, stepprod = 1.0;
         int cnt = 0;
         if (use_collapse && collapsed && all_obs) {
-            collapsed_step<M, K>(x, P, phi, q + M, yp, yv, [&](int i) { return cst[i]; }, sigma, stepprod, bad);
             cnt = M;
-            ++*n_collapsed;
+            if (frozen) {
+                // steady state: gains frozen at the values captured below
+                collapsed_frozen_step<M, K>(x, phi, yp, yv, [&](int i) { return cst[i]; }, sigma);
+                stepprod = frozen_prod;
+                ++*n_collapsed;   // (mode 3 reports frozen steps only, see below)
+            } else if (capture_next) {
+                collapsed_step_impl<M, K, true>(x, P, phi, q + M, yp, yv, [&](int i) { return cst[i]; },
+                                                [&](int i, double v) { cap[i] = v; }, sigma, stepprod, bad);
+                for (int i = 0; i < MT + K * M; ++i) cst[M * K + i] = cap[i];   // over S0 and QG
+                for (int j = 0; j < K; ++j)
+                    for (int l = j; l < K; ++l) P[tri<N>(M + j, M + l)] = Chold[tri<K>(j, l)];   // C is held
+                frozen_prod = stepprod;
+                frozen = true;
+                capture_next = false;
+            } else {
+                collapsed_step<M, K>(x, P, phi, q + M, yp, yv, [&](int i) { return cst[i]; }, sigma, stepprod, bad);
+                if (use_collapse != 3) ++*n_collapsed;
+                if (use_collapse == 3 && ++since_check == kCheckEvery) {
+                    // the kernel's test (there: once per tile and for all lanes of the warp)
+                    since_check = 0;
+                    const double cs = collapsed_checksum<M, K>(P);
+                    const bool same = fabs(cs - cchk) <= kFreezeTol * fabs(cs);
+                    cchk = cs;
+                    nconv = same ? nconv + 1 : 0;
+                    capture_next = nconv >= 2;
+                    if (capture_next)   // from here on the lane holds C (a warp may wait for its slowest lane)
+                        for (int j = 0; j < K; ++j)
+                            for (int l = j; l < K; ++l) Chold[tri<K>(j, l)] = P[tri<N>(M + j, M + l)];
+                }
+            }
         } else {
-            if (collapsed) collapsed_expand<M, K>(x, P, yp, [&](int i) { return G[i]; });
+            if (collapsed) {
+                if (frozen) collapsed_consts<M, K>(phi, q, G, [&](int i, double v) { cst[i] = v; });   // S0, QG back
+                collapsed_expand<M, K>(x, P, yp, [&](int i) { return G[i]; });
+            }
             collapsed = false;
+            frozen = false;
+            capture_next = false;
+            since_check = 0;
+            cchk = -1.0;
+            nconv = 0;
             for (int i = 0; i < N; ++i) x[i] *= phi[i];
             for (int r = 0; r < N; ++r)
                 for (int c = r; c < N; ++c) {

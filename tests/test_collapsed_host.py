@@ -94,6 +94,34 @@ def test_collapsed_matches_oracle(hostlib, k, pat):
                 assert ncol == T - 2
 
 
+@pytest.mark.parametrize("m,k", [(5, 3), (5, 1), (3, 2), (1, 1), (6, 2), (4, 3)])
+def test_steady_state_freeze_matches_oracle(hostlib, m, k):
+    """Mode 3 = the kernel's steady-state switch: once the factor covariance has stopped changing
+    the gains of one more full step are captured and later steps only touch the data.  Long series
+    so that the switch happens; gaps so that it is undone (constants restored, state expanded) and
+    happens again."""
+    rng = np.random.default_rng(7 * m + k)
+    T = 2400
+    G, phi, q = _model(rng, m, k)
+    H = np.concatenate([np.eye(m), G], axis=1)
+    x = np.zeros(m + k)
+    y = np.empty((T, m))
+    for t in range(T):
+        x = phi * x + np.sqrt(q) * rng.standard_normal(m + k)
+        y[t] = H @ x
+    for pat in ("dense", "gaps"):
+        yy = y.copy()
+        if pat == "gaps":
+            yy[1500:1503] = np.nan
+            yy[2000, 0] = np.nan
+        ref, _ = ko.filter_loglik(yy, np.diag(phi), np.diag(q), H, np.zeros(m), warmup=1)
+        got, nfrozen = _run(hostlib, yy, phi, q, G, 1, 3)
+        plain, _ = _run(hostlib, yy, phi, q, G, 1, 1)
+        assert abs(got - ref) <= 1e-11 * max(1.0, abs(ref)), (pat, got, ref)
+        assert abs(got - plain) <= 1e-12 * max(1.0, abs(ref))
+        assert nfrozen > T // 4, (pat, nfrozen)     # the switch did happen
+
+
 def test_collapsed_golden_dense(hostlib):
     """The committed fixture generated by the unmodified reference (tests/golden/make_golden.py)."""
     from conftest import load_cases
