@@ -516,12 +516,14 @@ def main():
                  "peak_source": "measured live by mkf_probe_fp64 (DFMA microbenchmark, same process)",
                  "algorithmic_flops_per_timestep_model": flops_per_step(n, m),
                  "ncu_pipe_fp64_cycles_active_pct": pipe_pct,
-                 "fp64_instructions_per_timestep_model": {"fully_observed_run": 312, "general_step": 538},
+                 "fp64_instructions_per_timestep_model": {"steady_state": 58, "fully_observed_run": 312,
+                                                          "general_step": 538},
                  "note": "frac > 1 because the kernel exploits the model structure: the reference's dense "
                          "n x n arithmetic is 1117.5 FMAs per unit; the structured full-state step executes 538 "
-                         "fp64 instructions and, in runs of fully observed steps (this workload), the "
-                         "factor-only step 312 (dfm_collapsed.cuh); ncu_pipe_* is the measured pipe occupancy "
-                         "of the last committed capture (profiles/)"},
+                         "fp64 instructions, the factor-only step of fully observed runs 312 and, once the factor "
+                         "covariance has converged, the steady-state step 58 (dfm_collapsed.cuh); ncu_pipe_* is "
+                         "the measured pipe occupancy of the last committed capture (profiles/), null when the "
+                         "current build has none"},
     }
 
     cpu = None
