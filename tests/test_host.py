@@ -239,3 +239,12 @@ def test_batched_fit_reaches_the_reference_optimum(eng, nbmodel):
     mdl.solve()
     assert np.all(np.abs(res.obj - mdl.parameters["obj_func"]) < 1e-4)
     np.testing.assert_allclose(res.alpha, np.tile(mdl.parameters["optimal"], (B, 1)), rtol=5e-3)
+
+
+@pytest.mark.parametrize("m,k", [(3, 2), (5, 3)])
+def test_steady_state_cases_are_sound(eng, m, k):
+    """The body of tests/test_gpu_kernels.py::test_dfm_steady_state_vs_oracle, run through the
+    oracle-backed stand-in: proves shapes, packing and tolerances of the check itself on the CPU."""
+    import steady_state_cases as ssc
+
+    ssc.check(eng, m, k, lambda t: t.cpu().numpy())
