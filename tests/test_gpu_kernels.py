@@ -211,15 +211,6 @@ def test_dfm_collapse_transitions_vs_oracle(eng, m, k, T):
     np.testing.assert_allclose(_np(mle_r), want, rtol=1e-12, atol=MLE_TOL)
 
 
-@pytest.mark.parametrize("m,k", [(3, 2), (6, 2), (2, 1), (4, 3), (5, 1), (1, 3), (5, 3)])
-def test_dfm_steady_state_vs_oracle(eng, m, k):
-    """T = 1500 fully observed steps: long enough for the steady-state step of the thread-per-model
-    kernel in every collapse-capable shape, with gaps that undo it."""
-    import steady_state_cases as ssc
-
-    ssc.check(eng, m, k, _np)
-
-
 def test_reduce_sum_deterministic(eng):
     v = torch.randn(100003, dtype=torch.float64, device=eng.device) * 1e3
     a = float(eng.reduce_sum(v)[0])
