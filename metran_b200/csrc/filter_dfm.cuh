@@ -24,6 +24,15 @@
 // (MKF_LOOKAHEAD=1: d_{i+1} = P h_{i+1} - g_i (d_i.h_{i+1}) computed while 1/f_i is in
 // flight) is kept for reference; it costs 44 more fp64 instructions per step and measured
 // 6 % slower than the plain order on B200 (profiles/r01_microbench_fp64.md).
+//
+// Three forms of the step, chosen by warp votes on the observations (R = 0, no history):
+//   full state   538 fp64 instructions at (M, K) = (5, 3): any pattern of missing values
+//   factor only  312: this and the previous step observed completely in every lane; the
+//                posterior is (c, C) = (x_c, P_cc), see dfm_collapsed.cuh
+//   steady state  58: additionally every lane's C has stopped changing; reciprocal pivots,
+//                multipliers and gains are constants captured from one factor-only step
+// The time loop is flattened over (tile, step) and written as a full-state loop with a nested
+// factor-only loop, so that P_ss, P_sc, x_s are dead registers in the latter.
 #pragma once
 #include <cuda.h>
 #include <string.h>
