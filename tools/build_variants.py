@@ -5,8 +5,8 @@ sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
     "base": [],
+    "nofreeze": ["-DMKF_FREEZE=0"],
     "nocollapse": ["-DMKF_COLLAPSE=0"],
-    "tt4": ["-DMKF_TT_ODD=4"],
 }
 out = os.path.join(ROOT, "metran_b200", "lib", "variants")
 os.makedirs(out, exist_ok=True)
