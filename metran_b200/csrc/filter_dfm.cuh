@@ -63,7 +63,10 @@ struct DfmArgs {
 };
 
 constexpr int kBlock = 32;  // one warp per CTA: CTAs spread evenly over the 592 SMSPs
-constexpr int kStages = 2;
+#ifndef MKF_STAGES
+#define MKF_STAGES 2   // ring depth; tiles are fetched MKF_STAGES - 1 ahead
+#endif
+constexpr int kStages = MKF_STAGES;
 #ifndef MKF_LOOKAHEAD
 #define MKF_LOOKAHEAD 0
 #endif
@@ -109,6 +112,12 @@ __host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false,
 
 #ifndef MKF_FREEZE
 #define MKF_FREEZE 1
+#endif
+#ifndef MKF_FREEZE_NCONV
+#define MKF_FREEZE_NCONV 2        // consecutive unchanged checks before a lane holds its covariance
+#endif
+#ifndef MKF_FREEZE_EVERY_STEP
+#define MKF_FREEZE_EVERY_STEP 0   // 1: check every step instead of once per tile (untested variant)
 #endif
 constexpr bool kFreeze = MKF_FREEZE != 0;
 constexpr double kFreezeTol = 8.8817841970012523e-16;   // 2^-50
@@ -321,8 +330,8 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     int tt = 0, steps = 0;
     const double *ys = myrow;
     double yv[M], yn[M];
-    auto open_tile = [&]() {   // start fetching tile + 1, wait for `tile`
-        issue_tile(tile + 1);
+    auto open_tile = [&]() {   // start fetching tile + kStages - 1, wait for `tile`
+        issue_tile(tile + kStages - 1);
         const int s = (int)(tile % kStages);
         if (tma) {
             mbar_wait(&bars[s], (unsigned)((tile / kStages) & 1));
@@ -379,7 +388,8 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         nobs += (t0 + tt >= a.warmup) ? cnt : 0;
     };
 
-    issue_tile(0);
+#pragma unroll
+    for (int s0 = 0; s0 < kStages - 1; ++s0) issue_tile(s0);
     bool more = ntiles > 0;
     if (more) {
         open_tile();
@@ -637,7 +647,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                                 frozen_prod = stepprod;
                                 frozen = true;
                                 capture_next = false;
-                            } else if (tt == 0) {
+                            } else if (MKF_FREEZE_EVERY_STEP || tt == 0) {
                                 // once per tile: a weighted sum of the entries of C (weights without
                                 // simple ratios, so that opposite drifts do not cancel) must not have
                                 // moved by more than 2^-50 of itself over two consecutive tiles
@@ -646,7 +656,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                                     const bool same = fabs(cs - cchk) <= kFreezeTol * fabs(cs);
                                     cchk = cs;
                                     nconv = same ? nconv + 1 : 0;
-                                    if (nconv >= 2) {
+                                    if (nconv >= MKF_FREEZE_NCONV) {
                                         lane_holds = true;
 #pragma unroll
                                         for (int j = 0; j < K; ++j)

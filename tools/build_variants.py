@@ -7,6 +7,10 @@ VARIANTS = {
     "base": [],
     "nofreeze": ["-DMKF_FREEZE=0"],
     "nocollapse": ["-DMKF_COLLAPSE=0"],
+    # candidates queued for round 2 (compile, never run on a GPU yet)
+    "rcp3": ["-DMKF_RCP3=1"],
+    "ring3x4": ["-DMKF_STAGES=3", "-DMKF_TT_ODD=4"],
+    "check1": ["-DMKF_FREEZE_EVERY_STEP=1", "-DMKF_FREEZE_NCONV=12"],
 }
 out = os.path.join(ROOT, "metran_b200", "lib", "variants")
 os.makedirs(out, exist_ok=True)
