@@ -3,6 +3,11 @@
 // the CUDA kernel (collapsed step when this and the previous step are fully observed,
 // expand + ordinary scalar updates otherwise), so that `pytest -m "not gpu"` can compare it
 // with the oracle.  Not part of the product library.
+//
+// use_collapse: 0 = full-state recursion only (the kernel's general path, structured updates),
+//               1 = + factor-only step in runs of fully observed steps,
+//               3 = + steady-state switch (convergence monitor, hold, capture, data-only step).
+// n_collapsed returns the number of factor-only steps (modes 0, 1) or of steady-state steps (3).
 #include <math.h>
 #include <stdint.h>
 
