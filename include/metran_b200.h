@@ -175,6 +175,17 @@ int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p,
                 const double *Hp, int64_t Hp_stride,
                 double *means_out, double *var_out, void *stream);
 
+/*
+ * mkf_dfm_loglik / mkf_dfm_loglik_alpha run long, fully observed series (R = 0) as three launches:
+ * transient kernel -> steady-state kernel -> resume kernel, exchanging one record per model through
+ * a library-owned device scratch buffer (grow-only, one per device and stream; no reference
+ * counterpart).  mkf_dfm_set_handoff(0) forces the single-kernel path (same results, bit for bit;
+ * used by the parity tests); returns the previous setting.  mkf_release_workspaces() frees the
+ * scratch buffers (call with the device idle).
+ */
+int mkf_dfm_set_handoff(int enabled);
+void mkf_release_workspaces(void);
+
 /* Deterministic (fixed-tree) sum of v[0..count) into out[0]; feeds the all-reduce. */
 int mkf_reduce_sum(const double *v, int64_t count, double *out, void *stream);
 

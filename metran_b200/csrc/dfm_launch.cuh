@@ -1,0 +1,78 @@
+// Host-side launch of the thread-per-model DFM kernels: dfm_loglik_kernel alone, or the
+// three-launch sequence  transient (hand-off on) -> steady state -> resume  (see dfm_steady.cuh).
+#pragma once
+#include "dfm_steady.cuh"
+
+namespace mkf_dfm {
+
+template <int M, int K, bool HASR, bool HIST>
+int launch_r(const DfmArgs &a0, cudaStream_t stream) {
+    DfmArgs a = a0;
+    alignas(64) CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    constexpr int TT = tile_steps(M, HIST);
+    const bool shared_y = a.y_stride == 0;
+    if (a.use_tma) {
+        int rc = make_y_tensor_map(&map, a.y, shared_y ? 1 : a.B, a.T * M, shared_y ? a.T * M : a.y_stride,
+                                   shared_y ? 1 : 32, TT * M);
+        if (rc != MKF_OK) a.use_tma = 0;  // cp.async staging instead
+    }
+    auto kern = dfm_loglik_kernel<M, K, HASR, HIST>;
+    const size_t smem = smem_bytes(M, K, HIST, !HASR && !HIST);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        mkf_host::set_cuda_error(e);
+        return MKF_ERR_CUDA;
+    }
+    const int64_t blocks = (a.B + kBlock - 1) / kBlock;
+    a.ho_mode = HO_MODE_OFF;
+
+    // Hand-off path: R = 0, no history, a collapse-capable shape, TMA staging and a series long
+    // enough for the transient to end well before T.
+    constexpr bool HO_OK = !HASR && !HIST && collapse_shape(M, K) && kFreeze;
+    if constexpr (HO_OK) {
+        using HO = Handoff<M, K>;
+        alignas(64) CUtensorMap smap;
+        memset(&smap, 0, sizeof(smap));
+        bool handoff = a.use_tma && handoff_enabled() && a.T >= 4 * kMinSteadySteps;
+        if (handoff)
+            handoff = make_y_tensor_map(&smap, a.y, shared_y ? 1 : a.B, a.T * M, shared_y ? a.T * M : a.y_stride,
+                                        shared_y ? 1 : 32, steady_tile_steps(M) * M) == MKF_OK;
+        if (handoff) {
+            const int64_t Bp = blocks * 32;
+            const size_t rec_bytes = (size_t)HO::NF * Bp * sizeof(double);
+            const size_t bytes = rec_bytes + (size_t)blocks * (sizeof(int64_t) + sizeof(int32_t)) + 64;
+            unsigned char *ws = static_cast<unsigned char *>(handoff_workspace(stream, bytes));
+            if (ws) {
+                a.ho_ws = reinterpret_cast<double *>(ws);
+                a.ho_pitch = Bp;
+                a.ho_tnext = reinterpret_cast<int64_t *>(ws + rec_bytes);
+                a.ho_state = reinterpret_cast<int32_t *>(ws + rec_bytes + (size_t)blocks * sizeof(int64_t));
+                auto skern = dfm_steady_kernel<M, K>;
+                const size_t ssmem = steady_smem_bytes(M);
+                e = cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+                if (e != cudaSuccess) {
+                    mkf_host::set_cuda_error(e);
+                    return MKF_ERR_CUDA;
+                }
+                a.ho_mode = HO_MODE_HANDOFF;   // every warp writes its ho_state: no memset needed
+                kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+                skern<<<(unsigned)blocks, 32, ssmem, stream>>>(a, smap);
+                a.ho_mode = HO_MODE_RESUME;
+                kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+                return mkf_host::check_launch();
+            }
+        }
+    }
+    kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+    return mkf_host::check_launch();
+}
+
+template <int M, int K>
+int launch(const DfmArgs &a, cudaStream_t stream) {
+    const bool hist = a.sigma || a.detf || a.cnt || a.fm || a.fc || a.pm || a.pc;
+    if (hist) return launch_r<M, K, true, true>(a, stream);
+    return a.r ? launch_r<M, K, true, false>(a, stream) : launch_r<M, K, false, false>(a, stream);
+}
+
+}  // namespace mkf_dfm

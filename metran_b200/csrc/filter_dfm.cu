@@ -1,7 +1,55 @@
 // C-ABI entry points of the thread-per-model DFM filter (see filter_dfm.cuh).
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "filter_dfm.cuh"
 
 namespace mkf_dfm {
+
+// ---- hand-off scratch: grow-only, one buffer per (device, stream) ------------------------------
+// Work enqueued on one stream is ordered, so consecutive calls on a stream can share one buffer;
+// calls on different streams may overlap and get their own.  Growing frees the old buffer with
+// cudaFree, which waits for the device: the work that used it has finished by then.
+namespace {
+struct Scratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+std::mutex g_ws_mutex;
+std::map<std::pair<int, cudaStream_t>, Scratch> g_ws;
+std::atomic<int> g_handoff{1};
+}  // namespace
+
+void *handoff_workspace(cudaStream_t stream, size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Scratch &s = g_ws[std::make_pair(dev, stream)];
+    if (s.bytes >= bytes) return s.ptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return nullptr;            // no allocation inside a graph capture: single-kernel path
+    }
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = nullptr;
+    s.bytes = 0;
+    const size_t want = bytes + bytes / 4;
+    if (cudaMalloc(&s.ptr, want) != cudaSuccess) {
+        (void)cudaGetLastError();
+        s.ptr = nullptr;
+        return nullptr;
+    }
+    s.bytes = want;
+    return s.ptr;
+}
+
+bool handoff_enabled() { return g_handoff.load() != 0; }
 
 // cuTensorMapEncodeTiled is a driver-API entry point; it is resolved through the runtime
 // (cudaGetDriverEntryPoint) so the library does not link libcuda directly.
@@ -107,6 +155,23 @@ extern "C" int mkf_dfm_filter_history(int64_t B, int64_t T, int32_t m, int32_t k
     a.mle = mle; a.nobs = nobs; a.status = status;
     a.sigma = sigma; a.detf = detf; a.cnt = cnt; a.fm = fm; a.fc = fc; a.pm = pm; a.pc = pc;
     return mkf_dfm::run(m, k, a, (cudaStream_t)stream);
+}
+
+extern "C" int mkf_dfm_set_handoff(int enabled) {
+    return mkf_dfm::g_handoff.exchange(enabled ? 1 : 0);
+}
+
+extern "C" void mkf_release_workspaces(void) {
+    std::lock_guard<std::mutex> lock(mkf_dfm::g_ws_mutex);
+    for (auto &kv : mkf_dfm::g_ws) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(kv.first.first);
+        if (kv.second.ptr) cudaFree(kv.second.ptr);
+        cudaSetDevice(cur);
+    }
+    mkf_dfm::g_ws.clear();
+    (void)cudaGetLastError();
 }
 
 extern "C" void mkf_limits(int32_t *n_max, int32_t *dfm_m_max, int32_t *dfm_k_max) {

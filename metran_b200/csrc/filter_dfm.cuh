@@ -60,6 +60,39 @@ struct DfmArgs {
     double *sigma, *detf;
     int32_t *cnt;
     double *fm, *fc, *pm, *pc;
+    // hand-off between this kernel and the steady-state kernel (dfm_steady.cuh); ho_mode 0 = off
+    int ho_mode;          // HO_MODE_*
+    double *ho_ws;        // records, field-major: ho_ws[field * ho_pitch + model]
+    int64_t ho_pitch;     // models rounded up to a multiple of 32
+    int64_t *ho_tnext;    // per warp: next time step to do
+    int32_t *ho_state;    // per warp: HO_*
+};
+
+enum { HO_MODE_OFF = 0, HO_MODE_HANDOFF = 1, HO_MODE_RESUME = 2 };
+enum { HO_DONE = 0, HO_STEADY = 1, HO_RESUME = 2 };
+// a warp is handed to the steady-state kernel only when at least this many steps remain
+constexpr int64_t kMinSteadySteps = 96;
+
+// Hand-off record of one model (doubles; the integers are small and exact in a double).
+template <int M, int K>
+struct Handoff {
+    static constexpr int N = M + K;
+    static constexpr int C = 0;                                   // factor means c[K]
+    static constexpr int CHOLD = C + K;                           // held factor covariance, packed upper [K(K+1)/2]
+    static constexpr int CONST = CHOLD + K * (K + 1) / 2;         // D[M*K], 1/f[M], multipliers, gains (dfm_collapsed.cuh)
+    static constexpr int NCONST = collapsed_const_count(M, K);
+    static constexpr int PHI = CONST + NCONST;                    // phi[N]
+    static constexpr int SUM_S = PHI + N;
+    static constexpr int SUM_C = SUM_S + 1;
+    static constexpr int FPROD = SUM_C + 1;
+    static constexpr int PEND_SIGMA = FPROD + 1;
+    static constexpr int PEND_PROD = PEND_SIGMA + 1;
+    static constexpr int FROZEN_PROD = PEND_PROD + 1;
+    static constexpr int FEXP = FROZEN_PROD + 1;
+    static constexpr int NOBS = FEXP + 1;
+    static constexpr int NSIG = NOBS + 1;
+    static constexpr int FLAGS = NSIG + 1;                        // bit 0: bad, bit 1: pend_on
+    static constexpr int NF = FLAGS + 1;
 };
 
 constexpr int kBlock = 32;  // one warp per CTA: CTAs spread evenly over the 592 SMSPs
@@ -163,6 +196,12 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     const int64_t b = b0 + lane;
     const bool active = b < a.B;
     if (b0 >= a.B) return;
+    // hand-off (only the R = 0, no-history builds of collapse-capable shapes take part)
+    constexpr bool HO_CAPABLE = !HASR && !HIST && collapse_shape(M, K) && kFreeze;
+    using HO = Handoff<M, K>;
+    const int64_t wid = b0 >> 5;
+    const int ho_mode = HO_CAPABLE ? a.ho_mode : HO_MODE_OFF;
+    if (ho_mode == HO_MODE_RESUME && a.ho_state[wid] != HO_RESUME) return;
     const bool tma = a.use_tma != 0;
     const bool shared_y = a.y_stride == 0;
 
@@ -287,10 +326,43 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     double pend_sigma = 0.0, pend_prod = 1.0;
 
     const int64_t T = a.T;
+    const double *yb = a.y + bb * a.y_stride;
+    // Resume mode: the steady-state kernel met a step with a missing value at time t_res and handed
+    // the warp back.  (c, held C, y(t_res - 1)) expand to the full posterior exactly as at a gap
+    // inside this kernel; the time loop then starts in the middle of tile t_res / TT.
+    int64_t t_res = 0;
+    if (ho_mode == HO_MODE_RESUME) {
+        if constexpr (HO_CAPABLE) {
+            const double *wsb = a.ho_ws + b;
+            const int64_t Bp = a.ho_pitch;
+            t_res = a.ho_tnext[wid];
+#pragma unroll
+            for (int j = 0; j < K; ++j) x[M + j] = wsb[(HO::C + j) * Bp];
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+#pragma unroll
+                for (int l = j; l < K; ++l) P[tri<N>(M + j, M + l)] = wsb[(HO::CHOLD + tri<K>(j, l)) * Bp];
+            sum_sigma.s = wsb[HO::SUM_S * Bp];
+            sum_sigma.c = wsb[HO::SUM_C * Bp];
+            fprod = wsb[HO::FPROD * Bp];
+            pend_sigma = wsb[HO::PEND_SIGMA * Bp];
+            pend_prod = wsb[HO::PEND_PROD * Bp];
+            fexp = (int)wsb[HO::FEXP * Bp];
+            nobs = (int)wsb[HO::NOBS * Bp];
+            nsig = (int)wsb[HO::NSIG * Bp];
+            const int fl = (int)wsb[HO::FLAGS * Bp];
+            bad = (fl & 1) != 0;
+            pend_on = (fl & 2) != 0;
+            double yq[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) yq[i] = yb[(t_res - 1) * M + i];
+            collapsed_expand<M, K>(x, P, yq, [&](int i) { return MKF_GG(i); });
+        }
+    }
     // (a box must start 16-byte aligned in global memory or the TMA engine faults with "illegal
     // instruction": TT*M is even for every M, see tile_steps)
-    const int64_t ntiles = (T + TT - 1) / TT;
-    const double *yb = a.y + bb * a.y_stride;
+    const int64_t tile_base = t_res / TT;                  // tiles are counted from here (mbarrier phases start at 0)
+    const int64_t ntiles = (T + TT - 1) / TT - tile_base;
     // shared y: the tile holds ONE row that every lane reads (broadcast)
     double *myrow = ring + ((shared_y && tma) || !active ? 0 : (size_t)lane * PITCH);  // + stage * 32 * PITCH
     constexpr unsigned kTileBytes = 32u * PITCH * 8u;
@@ -301,7 +373,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             return;
         }
         const int s = (int)(tile % kStages);
-        const int64_t tb = tile * TT;   // first step of the box
+        const int64_t tb = (tile_base + tile) * TT;   // first step of the box
         double *stage = ring + (size_t)s * 32 * PITCH;
         if (tma) {
             // WAR across proxies: the lanes' earlier LDS of this stage vs. the async write
@@ -339,7 +411,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             cp_async_wait<kStages - 1>();
         }
         ys = myrow + (size_t)s * 32 * PITCH;
-        t0 = tile * TT;
+        t0 = (tile_base + tile) * TT;
         steps = (int)min((int64_t)TT, T - t0);
         tt = 0;
     };
@@ -393,8 +465,9 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
     bool more = ntiles > 0;
     if (more) {
         open_tile();
+        tt = (int)(t_res - t0);          // 0 unless resuming in the middle of a tile
 #pragma unroll
-        for (int i = 0; i < M; ++i) yv[i] = ys[i];
+        for (int i = 0; i < M; ++i) yv[i] = ys[tt * M + i];
     }
     while (more) {
         bool warp_all;
@@ -580,7 +653,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 // lanes hold, one more full step stores their (now constant) reciprocal pivots,
                 // multipliers and gains and the warp switches to the data-only step.
                 constexpr int KT = K * (K + 1) / 2;
-                bool frozen = false, capture_next = false, lane_holds = false;
+                bool frozen = false, capture_next = false, lane_holds = false, handoff_now = false;
                 double frozen_prod = 1.0;
                 double cchk = -1.0;   // weighted sum of the entries of C at the last check
                 int nconv = 0;        // consecutive checks without change
@@ -646,6 +719,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                                 __syncwarp();
                                 frozen_prod = stepprod;
                                 frozen = true;
+                                handoff_now = true;
                                 capture_next = false;
                             } else if (MKF_FREEZE_EVERY_STEP || tt == 0) {
                                 // once per tile: a weighted sum of the entries of C (weights without
@@ -669,6 +743,42 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                         }
                     }
                     account(M, sigma, stepprod);
+                    if constexpr (HO_CAPABLE) {
+                        // every lane holds C and this step captured the constants: the rest of the
+                        // run (as long as it stays fully observed) is the steady-state kernel's
+                        if (ho_mode == HO_MODE_HANDOFF && handoff_now && T - (t0 + tt + 1) >= kMinSteadySteps) {
+                            double *wo = a.ho_ws + b;
+                            const int64_t Bp = a.ho_pitch;
+#pragma unroll
+                            for (int j = 0; j < K; ++j) wo[(HO::C + j) * Bp] = x[M + j];
+#pragma unroll
+                            for (int i = 0; i < KT; ++i) wo[(HO::CHOLD + i) * Bp] = Chold[i];
+#pragma unroll
+                            for (int i = 0; i < HO::NCONST; ++i) wo[(HO::CONST + i) * Bp] = lds_f64(ccs + i * 32);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) wo[(HO::PHI + i) * Bp] = phi[i];
+                            wo[HO::SUM_S * Bp] = sum_sigma.s;
+                            wo[HO::SUM_C * Bp] = sum_sigma.c;
+                            wo[HO::FPROD * Bp] = fprod;
+                            wo[HO::PEND_SIGMA * Bp] = pend_sigma;
+                            wo[HO::PEND_PROD * Bp] = pend_prod;
+                            wo[HO::FROZEN_PROD * Bp] = frozen_prod;
+                            wo[HO::FEXP * Bp] = (double)fexp;
+                            wo[HO::NOBS * Bp] = (double)nobs;
+                            wo[HO::NSIG * Bp] = (double)nsig;
+                            wo[HO::FLAGS * Bp] = (double)((bad ? 1 : 0) | (pend_on ? 2 : 0));
+                            if (lane == 0) {
+                                a.ho_tnext[wid] = t0 + tt + 1;
+                                a.ho_state[wid] = HO_STEADY;
+                            }
+                            // the loads still in flight target this CTA's shared memory: wait for them
+                            if (tma)
+                                for (int64_t r2 = tile + 1; r2 < min(tile + (int64_t)kStages, ntiles); ++r2)
+                                    mbar_wait(&bars[r2 % kStages], (unsigned)((r2 / kStages) & 1));
+                            return;
+                        }
+                        handoff_now = false;
+                    }
                     if (tt + 1 == steps) {
 #pragma unroll
                         for (int i = 0; i < M; ++i) yv[i] = yc[i];
@@ -692,42 +802,16 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         if (a.nobs) a.nobs[b] = (int64_t)nobs;
         if (a.status) a.status[b] = bad ? MKF_STATUS_NONPOSITIVE_F : 0;
     }
+    if (HO_CAPABLE && ho_mode != HO_MODE_OFF && lane == 0) a.ho_state[wid] = HO_DONE;
 }
 
 // Builds the tensor map of y viewed as [rows][row_elems] doubles (defined in filter_dfm.cu).
 int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
                       int box_rows, int box_elems);
-
-template <int M, int K, bool HASR, bool HIST>
-int launch_r(const DfmArgs &a0, cudaStream_t stream) {
-    DfmArgs a = a0;
-    alignas(64) CUtensorMap map;
-    memset(&map, 0, sizeof(map));
-    constexpr int TT = tile_steps(M, HIST);
-    if (a.use_tma) {
-        const bool shared_y = a.y_stride == 0;
-        int rc = make_y_tensor_map(&map, a.y, shared_y ? 1 : a.B, a.T * M, shared_y ? a.T * M : a.y_stride,
-                                   shared_y ? 1 : 32, TT * M);
-        if (rc != MKF_OK) a.use_tma = 0;  // cp.async staging instead
-    }
-    auto kern = dfm_loglik_kernel<M, K, HASR, HIST>;
-    const size_t smem = smem_bytes(M, K, HIST, !HASR && !HIST);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        mkf_host::set_cuda_error(e);
-        return MKF_ERR_CUDA;
-    }
-    const int64_t blocks = (a.B + kBlock - 1) / kBlock;
-    kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
-    return mkf_host::check_launch();
-}
-
-template <int M, int K>
-int launch(const DfmArgs &a, cudaStream_t stream) {
-    const bool hist = a.sigma || a.detf || a.cnt || a.fm || a.fc || a.pm || a.pc;
-    if (hist) return launch_r<M, K, true, true>(a, stream);
-    return a.r ? launch_r<M, K, true, false>(a, stream) : launch_r<M, K, false, false>(a, stream);
-}
+// Grow-only device scratch of the hand-off records, one per (device, stream); NULL when the allocation
+// fails (the caller then stays on the single-kernel path).  Defined in filter_dfm.cu.
+void *handoff_workspace(cudaStream_t stream, size_t bytes);
+bool handoff_enabled();
 
 // one translation unit per K instantiates M = 1..8 (keeps nvcc wall time parallel)
 template <int K>

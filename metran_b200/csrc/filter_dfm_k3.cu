@@ -1,5 +1,5 @@
 // Instantiates the thread-per-model DFM kernels for K = 3 common factors, M = 1..8 series.
-#include "filter_dfm.cuh"
+#include "dfm_launch.cuh"
 
 namespace mkf_dfm {
 template <>

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
                     const double yj = __shfl_sync(gmask, yv, jl, NP);
                     const double *hrow = sH + j * NP;
                     const double h_r = hrow[r];
-                    const double v = yj - group_sum<NP>(h_r * x);
+                    const double v = yj - group_sum<NP>(h_r * x, gmask);
                     double d;
                     if (NP >= 16) {
                         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) filter_generic_kernel(const FilterArgs a)
                             d = fma(P[c + 1], h01.y, d);
                         }
                     }
-                    const double f = sR[j] + group_sum<NP>(h_r * d);
+                    const double f = sR[j] + group_sum<NP>(h_r * d, gmask);
                     // one reciprocal serves k = d/f and v^2/f; f <= 0 or non-finite is flagged
                     // and poisons the result like the reference's log(f) (kalmanfilter.py:378)
                     const double rf = f_is_bad(f) ? nan("") : rcp_nr(f);

@@ -210,10 +210,12 @@ class SPKalmanFilter:
     # ---------------------------------------------------------------- reference surface
     def init_states(self):
         """Reset state means and covariances (kalmanfilter.py:506-518)."""
+        # the reference resets the six state arrays only: sigmas / detfs (and with them get_mle())
+        # survive.  A not yet materialised history therefore stays pending for sigmas / detfs,
+        # while the state arrays read as None until the next run.
         self._arrays = {k: v for k, v in getattr(self, "_arrays", {}).items() if k in ("sigmas_", "detfs_")}
         self._lazy = None
-        self._pending = None
-        self._mle_w1 = None
+        self._states_reset = True
         self.filtered_state_means = None
         self.filtered_state_covariances = None
         self.predicted_state_means = None
@@ -228,6 +230,8 @@ class SPKalmanFilter:
     def _get_array(self, name, key):
         if name in self._arrays:
             return self._arrays[name]
+        if getattr(self, "_states_reset", False):
+            return None
         if key in ("fm", "fc", "pm", "pc"):
             self._ensure_history()
         if self._lazy is not None and self._lazy.out.get(key) is not None:
@@ -239,13 +243,16 @@ class SPKalmanFilter:
         self._arrays[name] = value
 
     def _ensure_history(self):
+        """Run the history kernel for the run_filter() call still pending, on the SNAPSHOT of the
+        matrices, initial state and observations taken by that call."""
         if self._hist is None and getattr(self, "_pending", None) is not None:
-            out = self._filter_on_device(*self._pending)
+            out = self._filter_on_device(self._pending)
             cnt = out["cnt"][0].cpu().numpy()
             seen = cnt > 0
-            self._arrays["sigmas_"] = out["sigma"][0].cpu().numpy()[seen]
-            self._arrays["detfs_"] = out["detf"][0].cpu().numpy()[seen]
-            self._lazy = _LazyHistory(out)
+            self._arrays.setdefault("sigmas_", out["sigma"][0].cpu().numpy()[seen])
+            self._arrays.setdefault("detfs_", out["detf"][0].cpu().numpy()[seen])
+            if not getattr(self, "_states_reset", False):
+                self._lazy = _LazyHistory(out)
 
     def _get_series(self, name):
         if name not in self._arrays:
@@ -302,7 +309,11 @@ class SPKalmanFilter:
         y = np.where(observed, values, np.nan)
         eng = self._device_engine()
         self._y_dev = eng.tensor(y[None])
+        # results of a filter run on the previous observations must not be served for these
         self._hist = None
+        self._pending = None
+        self._mle_w1 = None
+        self._lazy = None
 
     def run_filter(self, initial_state_mean=None, initial_state_covariance=None, engine=None):
         """Run the Kalman filter (kalmanfilter.py:696-778) on the device."""
@@ -324,13 +335,14 @@ class SPKalmanFilter:
         self._hist = None
         self._mle_w1 = None
         self._pending = None
+        self._states_reset = False
         if self.filtermethod == self._filtermethod:
             # Device path.  What an objective evaluation needs (-2 log L, warmup = 1) is
             # computed now by the log-likelihood kernel; the history kernel that fills
-            # sigmas/detfs and the state arrays runs only if somebody reads them.
-            self._pending = (np.array(initial_state_mean, dtype=np.float64),
-                             np.array(initial_state_covariance, dtype=np.float64))
-            self._mle_w1 = self._loglik_on_device(*self._pending)
+            # sigmas/detfs and the state arrays runs only if somebody reads them -- on the
+            # snapshot taken here, whatever set_matrices()/set_observations() do in between.
+            self._pending = self._snapshot(initial_state_mean, initial_state_covariance)
+            self._mle_w1 = self._loglik_on_device(self._pending)
             return
         (sigmas, detfs, sigmacount, filtered_state_means, filtered_state_covariances,
          predicted_state_means, predicted_state_covariances) = self.filtermethod(
@@ -353,6 +365,15 @@ class SPKalmanFilter:
         eng = self._device_engine()
         h = self._hist
         A = np.ascontiguousarray(self.transition_matrix, dtype=np.float64)
+        if h is None:
+            # a plug-in filtermethod (kalmanfilter.py:761-771) left host arrays only: smooth those,
+            # as the reference's run_smoother does with whatever filter produced them (:685-691)
+            sm, sc = kalmansmoother_cuda(self.filtered_state_means, self.filtered_state_covariances,
+                                         self.predicted_state_means, self.predicted_state_covariances,
+                                         A, engine=eng)
+            self.smoothed_state_means = sm
+            self.smoothed_state_covariances = sc
+            return
         flags = h["flags"] & _lib.FLAG_A_DIAGONAL
         sm, sc, status = eng.smoother(h["fm"], h["fc"], h["pm"], h["pc"], A, flags=flags)
         if int(status[0]) & _lib.STATUS_CHOL_FAILED:
@@ -410,37 +431,40 @@ class SPKalmanFilter:
             return h["sm"], h["sc"]
         return self.smoothed_state_means[None], self.smoothed_state_covariances[None]
 
-    def _loglik_on_device(self, x0, P0):
-        """-2 log L (warmup = 1) of the current matrices: thread-per-model DFM kernel when
-        the model is Metran-shaped (metran.py:283-384) with the default initial state, else
-        the generic kernel."""
+    def _snapshot(self, x0, P0):
+        """Everything one filter run depends on, copied (host arrays) or referenced (the device
+        observations: set_observations() replaces the tensor, it never writes into it)."""
         eng = self._device_engine()
         if self._y_dev is None:
             self._y_dev = eng.tensor(unpack_observations(self.observations, self.observation_indices,
                                                          self.observation_count)[None])
-        A = np.ascontiguousarray(self.transition_matrix, dtype=np.float64)
-        Q = np.ascontiguousarray(self.transition_covariance, dtype=np.float64)
-        H = np.ascontiguousarray(self.observation_matrix, dtype=np.float64)
-        R = np.ascontiguousarray(self.observation_variance, dtype=np.float64)
+        return dict(x0=np.array(x0, dtype=np.float64), P0=np.array(P0, dtype=np.float64),
+                    A=np.array(self.transition_matrix, dtype=np.float64),
+                    Q=np.array(self.transition_covariance, dtype=np.float64),
+                    H=np.array(self.observation_matrix, dtype=np.float64),
+                    R=np.array(self.observation_variance, dtype=np.float64), y=self._y_dev)
+
+    def _loglik_on_device(self, snap):
+        """-2 log L (warmup = 1) of the snapshot: thread-per-model DFM kernel when the model is
+        Metran-shaped (metran.py:283-384) with the default initial state, else the generic
+        kernel."""
+        eng = self._device_engine()
+        A, Q, H, R, x0, P0 = (snap[k] for k in ("A", "Q", "H", "R", "x0", "P0"))
         m, n = H.shape
         flags = _structure_flags(A, Q)
         dfm = (flags == (_lib.FLAG_A_DIAGONAL | _lib.FLAG_Q_DIAGONAL) and m <= n
                and eng.dfm_supported(m, n - m) and np.array_equal(H[:, :m], np.eye(m))
                and not np.any(x0) and np.array_equal(P0, np.eye(n)))
         if dfm:
-            mle, _, _ = eng.dfm_loglik(self._y_dev, np.diag(A)[None].copy(), np.diag(Q)[None].copy(),
+            mle, _, _ = eng.dfm_loglik(snap["y"], np.diag(A)[None].copy(), np.diag(Q)[None].copy(),
                                        H[:, m:][None].copy(), r=R[None] if np.any(R) else None)
         else:
-            mle, _, _ = eng.filter_loglik(self._y_dev, A, Q, H, R, x0=x0[None], P0=P0[None], flags=flags)
+            mle, _, _ = eng.filter_loglik(snap["y"], A, Q, H, R, x0=x0[None], P0=P0[None], flags=flags)
         return float(mle[0])
 
-    def _filter_on_device(self, x0, P0):
+    def _filter_on_device(self, snap):
         eng = self._device_engine()
-        if self._y_dev is None:
-            self._y_dev = eng.tensor(unpack_observations(self.observations, self.observation_indices,
-                                                         self.observation_count)[None])
-        out = _filter_device(eng, self._y_dev, self.transition_matrix, self.transition_covariance,
-                             self.observation_matrix, self.observation_variance, x0, P0)
+        out = _filter_device(eng, snap["y"], snap["A"], snap["Q"], snap["H"], snap["R"], snap["x0"], snap["P0"])
         self._hist = out
         return out
 

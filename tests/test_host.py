@@ -139,6 +139,64 @@ def test_engine_error_behaviour(eng, b21):
     assert kf.filtered_state_means.shape == (50, 6)
 
 
+def test_run_smoother_with_plugin_filtermethod(eng, b21):
+    """A plug-in filtermethod (the reference's own extension point, kalmanfilter.py:501-504,
+    761-771) leaves host arrays only; run_smoother must smooth those like the reference does
+    (:685-691).  Both the advertised seqkalmanfilter_cuda and a plain Python callable."""
+    from functools import partial
+
+    from metran_b200.kalmanfilter import SPKalmanFilter, seqkalmanfilter_cuda
+
+    g = b21
+    for method in (partial(seqkalmanfilter_cuda, engine=eng), ko.seqkalmanfilter):
+        kf = SPKalmanFilter(device_engine=eng)
+        kf.set_observations(g["y"])
+        kf.set_matrices(g["A_opt"], g["Q_opt"], g["H_opt"], g["R_opt"])
+        kf.filtermethod = method
+        kf.run_filter()
+        np.testing.assert_allclose(kf.sigmas, g["sigmas"], atol=1e-12)
+        assert abs(kf.get_mle() - float(g["mle_opt"])) < 1e-9
+        kf.run_smoother()
+        np.testing.assert_allclose(kf.smoothed_state_means, g["sm_full"], atol=1e-11)
+        np.testing.assert_allclose(kf.smoothed_state_covariances[g["sel"]], g["sc"], atol=1e-11)
+        means, _ = kf.simulate(g["H_opt"] * g["oseries_std"][:, None])
+        np.testing.assert_allclose(np.asarray(means)[g["sel"]] + g["oseries_mean"], g["sim_means"], atol=1e-10)
+
+
+def test_lazy_history_is_a_snapshot(eng, b21):
+    """run_filter() defers the history kernel; what is read later must belong to the matrices and
+    observations of THAT call, whatever set_matrices()/init_states() did in between, and
+    set_observations() must drop the cached likelihood of the previous data."""
+    from metran_b200.kalmanfilter import SPKalmanFilter
+
+    g = b21
+    kf = SPKalmanFilter(device_engine=eng)
+    kf.set_observations(g["y"])
+    kf.set_matrices(g["A_opt"], g["Q_opt"], g["H_opt"], g["R_opt"])
+    kf.run_filter()
+    mle = kf.get_mle()
+    kf.set_matrices(0.5 * g["A_opt"], g["Q_opt"], g["H_opt"], g["R_opt"])     # no run_filter()
+    np.testing.assert_allclose(kf.sigmas, g["sigmas"], atol=1e-12)
+    np.testing.assert_allclose(kf.filtered_state_means[g["sel"]], g["fm"], atol=1e-11)
+    assert kf.get_mle() == mle
+    # init_states(): state arrays gone, sigmas / detfs / get_mle() survive (kalmanfilter.py:506-518)
+    kf.set_matrices(g["A_opt"], g["Q_opt"], g["H_opt"], g["R_opt"])
+    kf.run_filter()
+    kf.init_states()
+    assert kf.filtered_state_means is None and kf.smoothed_state_covariances is None
+    assert kf.get_mle() == mle
+    np.testing.assert_allclose(kf.detfs, g["detfs"], atol=1e-12)
+    assert abs(kf.get_mle(warmup=3) - (np.sum(g["observation_count"][3:]) * np.log(2 * np.pi)
+                                       + g["detfs"][3:].sum() + g["sigmas"][3:].sum())) < 1e-9
+    assert kf.filtered_state_means is None
+    # new observations: nothing of the old run may be served
+    kf.run_filter()
+    kf.set_observations(g["y"][:100])
+    assert kf._mle_w1 is None and kf._pending is None
+    kf.run_filter()
+    assert kf.filtered_state_means.shape == (100, 6)
+
+
 # ---------------------------------------------------------------- Metran-facing mirror
 def test_dfm_objective_and_batch(eng, b21):
     from metran_b200.dfm import DynamicFactorModel

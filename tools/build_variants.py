@@ -5,13 +5,17 @@ sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
     "base": [],
-    "nofreeze": ["-DMKF_FREEZE=0"],
-    "nocollapse": ["-DMKF_COLLAPSE=0"],
-    # candidates queued for round 2 (compile, never run on a GPU yet)
-    "rcp3": ["-DMKF_RCP3=1"],
-    "ring3x4": ["-DMKF_STAGES=3", "-DMKF_TT_ODD=4"],
-    "check1": ["-DMKF_FREEZE_EVERY_STEP=1", "-DMKF_FREEZE_NCONV=12"],
+    # steady-state kernel (dfm_steady.cuh): tile length x ring depth, resident CTAs per SM
+    "st_2x4": ["-DMKF_ST_TT=2", "-DMKF_ST_STAGES=4"],
+    "st_2x10": ["-DMKF_ST_TT=2", "-DMKF_ST_STAGES=10"],
+    "st_4x4": ["-DMKF_ST_TT=4", "-DMKF_ST_STAGES=4"],
+    "st_6x3": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=3"],
+    "st_6x4_minb8": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=4", "-DMKF_ST_MINB=8"],
+    "st_2x6_minb8": ["-DMKF_ST_MINB=8"],
+    "st_2x6_minb16": ["-DMKF_ST_MINB=16"],
 }
+if len(sys.argv) > 1:
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}
 out = os.path.join(ROOT, "metran_b200", "lib", "variants")
 os.makedirs(out, exist_ok=True)
 srcs = ["api.cu", "filter_dfm.cu", "filter_dfm_k0.cu", "filter_dfm_k1.cu", "filter_dfm_k2.cu", "filter_dfm_k3.cu"]
