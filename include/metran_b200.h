@@ -185,6 +185,16 @@ int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p,
  */
 int mkf_dfm_set_handoff(int enabled);
 void mkf_release_workspaces(void);
+/*
+ * Measurement aid for the three-launch path (no reference counterpart).  With
+ * mkf_dfm_set_profile(1) the library records CUDA events around each launch; afterwards
+ * mkf_dfm_last_profile(stream, ms, stats) waits for `stream` and returns for the most recent
+ * three-launch call on it: ms[3] = device time of the transient, steady-state and resume kernels
+ * (-1 when not recorded); stats[3] = {warps, warps handed to the steady-state kernel, warp-steps done
+ * after the hand-off}.  Either output pointer may be NULL.  MKF_ERR_BAD_ARG when no such call exists.
+ */
+int mkf_dfm_set_profile(int enabled);
+int mkf_dfm_last_profile(void *stream, float *ms, int64_t *stats);
 
 /* Deterministic (fixed-tree) sum of v[0..count) into out[0]; feeds the all-reduce. */
 int mkf_reduce_sum(const double *v, int64_t count, double *out, void *stream);

@@ -39,6 +39,8 @@ SIGNATURES = {
     "mkf_project": (ctypes.c_int, [_i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "mkf_dfm_set_handoff": (ctypes.c_int, [ctypes.c_int]),
     "mkf_release_workspaces": (None, []),
+    "mkf_dfm_set_profile": (ctypes.c_int, [ctypes.c_int]),
+    "mkf_dfm_last_profile": (ctypes.c_int, [_ptr, _ptr, _ptr]),
     "mkf_reduce_sum": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr]),
     "mkf_probe_fp64": (ctypes.c_int, [_i32, _i32, _ptr, _ptr]),
 }

@@ -301,6 +301,29 @@ class KalmanEngine:
         main.synchronize()
         return res
 
+    def set_handoff(self, enabled):
+        """Three-launch path of the DFM log-likelihood (transient -> steady state -> resume) on/off;
+        returns the previous setting.  Results are bit-identical either way."""
+        return bool(self.lib.mkf_dfm_set_handoff(1 if enabled else 0))
+
+    def dfm_profile(self, fn):
+        """Run ``fn()`` (one DFM log-likelihood call) with per-launch CUDA events recorded inside the
+        library; returns {"ms": [transient, steady, resume], "warps", "warps_handed_off",
+        "warp_steps_after_handoff"} or None when the call took the single-kernel path."""
+        prev = self.lib.mkf_dfm_set_profile(1)
+        try:
+            fn()
+            ms = (ctypes.c_float * 3)()
+            st = (ctypes.c_int64 * 3)()
+            rc = self.lib.mkf_dfm_last_profile(self._stream(), ctypes.cast(ms, ctypes.c_void_p),
+                                               ctypes.cast(st, ctypes.c_void_p))
+        finally:
+            self.lib.mkf_dfm_set_profile(prev)
+        if rc != _lib.MKF_OK or ms[0] < 0:
+            return None
+        return {"ms": [float(v) for v in ms], "warps": int(st[0]), "warps_handed_off": int(st[1]),
+                "warp_steps_after_handoff": int(st[2])}
+
     def probe_fp64_tflops(self, blocks=148 * 8, iters=4096, reps=5):
         """Measured fp64 FMA throughput (TFLOP/s) of this device: roofline denominator."""
         scratch = self.empty(1)

@@ -42,8 +42,9 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
             const int64_t Bp = blocks * 32;
             const size_t rec_bytes = (size_t)HO::NF * Bp * sizeof(double);
             const size_t bytes = rec_bytes + (size_t)blocks * (sizeof(int64_t) + sizeof(int32_t)) + 64;
-            unsigned char *ws = static_cast<unsigned char *>(handoff_workspace(stream, bytes));
-            if (ws) {
+            HandoffScratch *hs = handoff_scratch(stream, bytes);
+            if (hs) {
+                unsigned char *ws = static_cast<unsigned char *>(hs->ptr);
                 a.ho_ws = reinterpret_cast<double *>(ws);
                 a.ho_pitch = Bp;
                 a.ho_tnext = reinterpret_cast<int64_t *>(ws + rec_bytes);
@@ -55,11 +56,20 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
                     mkf_host::set_cuda_error(e);
                     return MKF_ERR_CUDA;
                 }
+                hs->blocks = blocks;
+                hs->T = a.T;
+                hs->tnext = a.ho_tnext;
+                const bool prof = profile_enabled() && profile_events(hs);
                 a.ho_mode = HO_MODE_HANDOFF;   // every warp writes its ho_state: no memset needed
+                if (prof) cudaEventRecord(hs->ev[0], stream);
                 kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+                if (prof) cudaEventRecord(hs->ev[1], stream);
                 skern<<<(unsigned)blocks, 32, ssmem, stream>>>(a, smap);
+                if (prof) cudaEventRecord(hs->ev[2], stream);
                 a.ho_mode = HO_MODE_RESUME;
                 kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+                if (prof) cudaEventRecord(hs->ev[3], stream);
+                hs->profiled = prof;
                 return mkf_host::check_launch();
             }
         }

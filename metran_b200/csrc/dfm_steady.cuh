@@ -29,15 +29,31 @@ namespace mkf_dfm {
 #define MKF_ST_TT 2        // time steps per tile of the steady kernel (M*TT even: 16-byte rows)
 #endif
 #ifndef MKF_ST_STAGES
-#define MKF_ST_STAGES 6    // ring depth: all stages are in flight while one is being consumed
+#define MKF_ST_STAGES 8    // ring depth: all stages are in flight while one tile sits in registers
+#endif
+#ifndef MKF_ST_PROXY_FENCE
+#define MKF_ST_PROXY_FENCE 1   // fence.proxy.async between a tile's LDS and the TMA refill of its stage
 #endif
 #ifndef MKF_ST_MINB
-#define MKF_ST_MINB 12     // resident one-warp CTAs per SM the register allocation must allow
+#define MKF_ST_MINB 8      // resident one-warp CTAs per SM the register allocation must allow
 #endif
 
 __host__ __device__ constexpr int steady_tile_steps(int M) { return (M % 2 == 1 && MKF_ST_TT % 2 == 1) ? MKF_ST_TT + 1 : MKF_ST_TT; }
 __host__ __device__ constexpr size_t steady_smem_bytes(int M) {
     return 128 + (size_t)MKF_ST_STAGES * 32 * steady_tile_steps(M) * M * sizeof(double) + MKF_ST_STAGES * sizeof(uint64_t);
+}
+
+// One elected lane of the (converged) warp: SASS ELECT, no divergence loop around the TMA issue.
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 template <int M, int K>
@@ -60,8 +76,9 @@ __global__ void __launch_bounds__(32, MKF_ST_MINB) dfm_steady_kernel(const DfmAr
     const int64_t b = b0 + lane;
     const bool active = b < a.B;
     const bool shared_y = a.y_stride == 0;
-    const int64_t T = a.T;
-    const int64_t t_begin = a.ho_tnext[w];
+    // time indices fit 32 bits: the tensor map of y needs T * M < 2^31 (make_y_tensor_map)
+    const int T = (int)a.T;
+    const int t_begin = (int)a.ho_tnext[w];
     const double *wsb = a.ho_ws + b;          // field f of this lane: wsb[f * Bp]
     const int64_t Bp = a.ho_pitch;
 
@@ -73,19 +90,27 @@ __global__ void __launch_bounds__(32, MKF_ST_MINB) dfm_steady_kernel(const DfmAr
     __syncwarp();
 
     // ---- tiles on the absolute grid of TT steps; the first and the last may be partial -------------
-    const int64_t tile0 = t_begin / TT;
-    const int64_t ntiles = (T + TT - 1) / TT - tile0;      // >= 1: the full kernel hands off only with steps left
-    const double *myrow = ring + ((shared_y || !active) ? 0 : (size_t)lane * PITCH);
-    constexpr unsigned kTileBytes = 32u * PITCH * 8u;
-    auto issue = [&](int64_t rel) {   // caller: lane 0 only, stage free, rel < ntiles
-        const int s = (int)(rel % S);
-        mbar_arrive_expect_tx(&bars[s], shared_y ? (unsigned)(PITCH * 8) : kTileBytes);
-        tma_load_2d(ring + (size_t)s * 32 * PITCH, &ymap, (int)((tile0 + rel) * TT * M), shared_y ? 0 : (int)b0, &bars[s]);
+    const int tile0 = t_begin / TT;
+    const int ntiles = (T + TT - 1) / TT - tile0;      // >= 1: the full kernel hands off only with steps left
+    const unsigned row_off = (shared_y || !active) ? 0u : (unsigned)lane * PITCH * 8u;
+    const unsigned ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    constexpr unsigned kStageBytes = 32u * PITCH * 8u;
+    const unsigned tx_bytes = shared_y ? (unsigned)(PITCH * 8) : kStageBytes;
+    const int row0 = shared_y ? 0 : (int)b0;
+    // refill of stage s with tile `rel` (one elected lane; the stage must be free)
+    auto issue = [&](int s, int rel) {
+        const unsigned bar = bars_u32 + 8u * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(tx_bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                ring_u32 + kStageBytes * s),
+            "l"(&ymap), "r"((tile0 + rel) * (TT * M)), "r"(row0), "r"(bar)
+            : "memory");
     };
-    if (lane == 0) {
+    if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < S; ++s)
-            if (s < ntiles) issue(s);
+            if (s < ntiles) issue(s, s);
     }
 
     // ---- hand-off record -> registers (overlaps the first tiles' flight) ----------------------------
@@ -112,97 +137,152 @@ __global__ void __launch_bounds__(32, MKF_ST_MINB) dfm_steady_kernel(const DfmAr
     const int fl = (int)wsb[HO::FLAGS * Bp];
     const bool bad = (fl & 1) != 0;
     bool pend_on = (fl & 2) != 0;
+    const int warmup = a.warmup;
 
     // y(t_begin - 1): straight from global memory, once (t_begin >= 1 by construction)
     double yp[M];
     {
-        const double *yb = a.y + (active ? b : b0) * a.y_stride + (t_begin - 1) * M;
+        const double *yb = a.y + (active ? b : b0) * a.y_stride + (int64_t)(t_begin - 1) * M;
 #pragma unroll
         for (int i = 0; i < M; ++i) yp[i] = yb[i];
     }
 
-    auto fold = [&]() {
-        sum_sigma.add(pend_on ? pend_sigma : 0.0);
-        fprod *= pend_on ? pend_prod : 1.0;
+    // The exponent of the running product of the innovation variances is peeled off once per tile
+    // (an exact scaling: the mantissa bits and the summed exponent do not depend on when it happens).
+    auto peel = [&]() {
         const int hi = __double2hiint(fprod);
         const int ex = ((hi >> 20) & 0x7ff) - 1023;
         fexp += ex;
         fprod = __hiloint2double(hi - (ex << 20), __double2loint(fprod));
     };
     // one steady step at absolute time t (the arithmetic and its order are dfm_loglik_kernel's)
-    auto step = [&](const double *yc, int64_t t) {
-        fold();
+    auto step = [&](const double *yc, int t) {
+        sum_sigma.add(pend_on ? pend_sigma : 0.0);
+        fprod *= pend_on ? pend_prod : 1.0;
         double sigma = 0.0;
         collapsed_frozen_step<M, K>(x, phi, yp, yc, [&](int i) { return cst[i]; }, sigma);
-        pend_on = nsig >= a.warmup;
+        pend_on = nsig >= warmup;
         pend_sigma = sigma;
         pend_prod = frozen_prod;
         nsig += 1;
-        nobs += (t >= a.warmup) ? M : 0;
+        nobs += (t >= warmup) ? M : 0;
 #pragma unroll
         for (int i = 0; i < M; ++i) yp[i] = yc[i];
     };
 
-    int64_t t = t_begin;           // next step to do
-    int64_t rel = 0;
+    int t = t_begin;             // next step to do
     bool gap = false;
-    for (; rel < ntiles; ++rel) {
-        const int s = (int)(rel % S);
-        mbar_wait(&bars[s], (unsigned)((rel / S) & 1));
-        const int64_t ts = (tile0 + rel) * TT;           // first step of the tile
-        const int lo = (int)(t - ts);                     // > 0 only in the first tile
-        const int hi = (int)min((int64_t)TT, T - ts);     // < TT only in the last tile
-        // the whole tile -> registers (128-bit LDS: rows are 16-byte aligned, PITCH is even)
-        double yt[PITCH];
-        {
-            const double2 *src = reinterpret_cast<const double2 *>(myrow + (size_t)s * 32 * PITCH);
+    // wait for stage s and pull its tile into registers (128-bit LDS: rows are 16-byte aligned)
+    auto load_tile = [&](int s, unsigned parity, double *yt) {
+        const unsigned bar = bars_u32 + 8u * s;
+        unsigned ok;
+        do {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        } while (!ok);
+        const unsigned src = ring_u32 + kStageBytes * s + row_off;
 #pragma unroll
-            for (int e = 0; e < PITCH / 2; ++e) {
-                const double2 v = src[e];
-                yt[2 * e] = v.x;
-                yt[2 * e + 1] = v.y;
-            }
+        for (int e = 0; e < PITCH / 2; ++e)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(yt[2 * e]), "=d"(yt[2 * e + 1]) : "r"(src + 16u * e));
+    };
+    // One FULL tile (all TT steps inside [t, T)): validate every step (all M series observed in all
+    // 32 lanes; one vote over the whole tile), refill the stage, apply the steps.  The vote depends
+    // on every lane's loads, so it also orders those loads before the refill; the proxy fence makes
+    // that ordering visible to the async (TMA) proxy.  A tile with an incomplete step is left to
+    // slow_tile: it is NOT refilled, so S - 1 loads are then in flight, the ones the exit path waits
+    // for.  Called with a literal s in the unrolled main loop, where all addressing folds to
+    // immediates.
+    auto fast_tile = [&](int s, unsigned parity, int rel) {
+        double yt[PITCH];
+        load_tile(s, parity, yt);
+        unsigned ok = 1u;
+#pragma unroll
+        for (int e = 0; e < PITCH; ++e) ok &= is_observed(yt[e]) ? 1u : 0u;
+        if (!__all_sync(0xffffffffu, ok != 0u)) {
+            gap = true;
+            return;
         }
-        // stage s is free again: refill it with tile rel + S (WAR across proxies: fence, then issue)
+#if MKF_ST_PROXY_FENCE
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncwarp();
-        if (lane == 0 && rel + S < ntiles) issue(rel + S);
-        // validate before applying: step u of the tile counts when every lane observed all M series
-        // (one vote per step, taken for the whole tile up front)
-        bool full = true;        // warp-uniform: all steps [lo, hi) of the tile are complete
-        int nok = hi;            // first incomplete step (warp-uniform)
+#endif
+        if (rel + S < ntiles) {
+            if (elect_one()) issue(s, rel + S);
+        }
+        const int ts = (tile0 + rel) * TT;
+#pragma unroll
+        for (int u = 0; u < TT; ++u) step(yt + u * M, ts + u);
+        peel();
+        t = ts + TT;
+    };
+    // Any tile: partial on the left (first tile), on the right (last tile), or with an incomplete
+    // step; applies the complete steps in front of the first incomplete one and reports the gap.
+    auto slow_tile = [&](int s, unsigned parity, int rel) {
+        const int ts = (tile0 + rel) * TT;
+        const int lo = max(t - ts, 0), hi = min(TT, T - ts);
+        double yt[PITCH];
+        load_tile(s, parity, yt);
+        int nok = hi;            // first incomplete step in [lo, hi) (warp-uniform)
 #pragma unroll
         for (int u = TT - 1; u >= 0; --u) {
             unsigned ok = 1u;
 #pragma unroll
             for (int i = 0; i < M; ++i) ok &= is_observed(yt[u * M + i]) ? 1u : 0u;
             const bool all = __all_sync(0xffffffffu, ok != 0u);
-            if (!all && u >= lo && u < hi) {
-                full = false;
-                nok = u;
+            if (!all && u >= lo && u < hi) nok = u;
+        }
+        if (nok == hi) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            if (rel + S < ntiles) {
+                if (elect_one()) issue(s, rel + S);
             }
         }
-        if (full && lo == 0 && hi == TT) {
 #pragma unroll
-            for (int u = 0; u < TT; ++u) step(yt + u * M, ts + u);
-        } else {
+        for (int u = 0; u < TT; ++u)
+            if (u >= lo && u < nok) step(yt + u * M, ts + u);
+        peel();
+        t = ts + nok;
+        gap = nok != hi;
+    };
+
+    // the first S tiles (run-time stage; the first may start in the middle), then groups of S full
+    // tiles with compile-time stages, then the rest (the last tile may be partial)
+    int rel = 0;
+    const int nfull = (T / TT) - tile0;          // tiles [1, nfull) are complete on both sides
+#pragma unroll 1
+    for (; !gap && rel < min(S, ntiles); ++rel) slow_tile(rel, 0u, rel);
+    unsigned parity = 1u;
+    while (!gap && rel + S <= nfull) {
 #pragma unroll
-            for (int u = 0; u < TT; ++u)
-                if (u >= lo && u < nok) step(yt + u * M, ts + u);
+        for (int s = 0; s < S; ++s) {
+            if (!gap) fast_tile(s, parity, rel + s);
         }
-        if (!full) {
-            t = ts + nok;
-            gap = true;
+        if (gap) {
+            rel = t / TT - tile0;                // the tile fast_tile refused: still in its stage
+            slow_tile(rel % S, parity, rel);
             break;
         }
-        t = ts + hi;
+        rel += S;
+        parity ^= 1u;
+    }
+    if (!gap) {
+        // rel is a multiple of S; fewer than S full tiles and possibly a partial one remain
+#pragma unroll 1
+        for (int s = 0; !gap && rel < ntiles; ++s, ++rel) slow_tile(s, parity, rel);
     }
 
     if (gap) {
         // drain the loads still in flight (their destination is this CTA's shared memory), then hand
         // the warp back: c, the running sums and the position; held C, phi and the constants are
         // still in the record
-        for (int64_t r2 = rel + 1; r2 < min(rel + S, ntiles); ++r2) mbar_wait(&bars[r2 % S], (unsigned)((r2 / S) & 1));
+        const int rel_gap = t / TT - tile0;            // the tile that held the incomplete step
+        for (int r2 = rel_gap + 1; r2 < min(rel_gap + S, ntiles); ++r2) mbar_wait(&bars[r2 % S], (unsigned)((r2 / S) & 1));
         double *wo = a.ho_ws + b;
 #pragma unroll
         for (int j = 0; j < K; ++j) wo[(HO::C + j) * Bp] = x[M + j];

@@ -13,24 +13,22 @@ namespace mkf_dfm {
 // calls on different streams may overlap and get their own.  Growing frees the old buffer with
 // cudaFree, which waits for the device: the work that used it has finished by then.
 namespace {
-struct Scratch {
-    void *ptr = nullptr;
-    size_t bytes = 0;
-};
 std::mutex g_ws_mutex;
-std::map<std::pair<int, cudaStream_t>, Scratch> g_ws;
+std::map<std::pair<int, cudaStream_t>, HandoffScratch> g_ws;
 std::atomic<int> g_handoff{1};
+std::atomic<int> g_profile{0};
 }  // namespace
 
-void *handoff_workspace(cudaStream_t stream, size_t bytes) {
+HandoffScratch *handoff_scratch(cudaStream_t stream, size_t bytes) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
         (void)cudaGetLastError();
         return nullptr;
     }
     std::lock_guard<std::mutex> lock(g_ws_mutex);
-    Scratch &s = g_ws[std::make_pair(dev, stream)];
-    if (s.bytes >= bytes) return s.ptr;
+    HandoffScratch &s = g_ws[std::make_pair(dev, stream)];
+    s.profiled = false;
+    if (s.bytes >= bytes) return &s;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
         (void)cudaGetLastError();
@@ -46,7 +44,20 @@ void *handoff_workspace(cudaStream_t stream, size_t bytes) {
         return nullptr;
     }
     s.bytes = want;
-    return s.ptr;
+    return &s;
+}
+
+bool profile_enabled() { return g_profile.load() != 0; }
+bool profile_events(HandoffScratch *s) {
+    if (!s->have_events) {
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreate(&s->ev[i]) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return false;
+            }
+        s->have_events = true;
+    }
+    return true;
 }
 
 bool handoff_enabled() { return g_handoff.load() != 0; }
@@ -161,6 +172,53 @@ extern "C" int mkf_dfm_set_handoff(int enabled) {
     return mkf_dfm::g_handoff.exchange(enabled ? 1 : 0);
 }
 
+extern "C" int mkf_dfm_set_profile(int enabled) { return mkf_dfm::g_profile.exchange(enabled ? 1 : 0); }
+
+extern "C" int mkf_dfm_last_profile(void *stream, float *ms, int64_t *stats) {
+    using namespace mkf_dfm;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return MKF_ERR_CUDA;
+    HandoffScratch snap;
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mutex);
+        auto it = g_ws.find(std::make_pair(dev, (cudaStream_t)stream));
+        if (it == g_ws.end() || !it->second.ptr || it->second.blocks <= 0) return MKF_ERR_BAD_ARG;
+        snap = it->second;
+    }
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        mkf_host::set_cuda_error(e);
+        return MKF_ERR_CUDA;
+    }
+    if (ms) {
+        for (int i = 0; i < 3; ++i) {
+            ms[i] = -1.0f;
+            if (snap.profiled) cudaEventElapsedTime(&ms[i], snap.ev[i], snap.ev[i + 1]);
+        }
+    }
+    if (stats) {
+        int64_t *tn = new int64_t[snap.blocks];
+        e = cudaMemcpy(tn, snap.tnext, sizeof(int64_t) * snap.blocks, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            delete[] tn;
+            mkf_host::set_cuda_error(e);
+            return MKF_ERR_CUDA;
+        }
+        int64_t handed = 0, steps = 0;
+        for (int64_t w = 0; w < snap.blocks; ++w)
+            if (tn[w] < snap.T) {
+                ++handed;
+                steps += snap.T - tn[w];
+            }
+        delete[] tn;
+        stats[0] = snap.blocks;
+        stats[1] = handed;
+        stats[2] = steps;
+    }
+    (void)cudaGetLastError();
+    return MKF_OK;
+}
+
 extern "C" void mkf_release_workspaces(void) {
     std::lock_guard<std::mutex> lock(mkf_dfm::g_ws_mutex);
     for (auto &kv : mkf_dfm::g_ws) {
@@ -168,6 +226,8 @@ extern "C" void mkf_release_workspaces(void) {
         cudaGetDevice(&cur);
         cudaSetDevice(kv.first.first);
         if (kv.second.ptr) cudaFree(kv.second.ptr);
+        if (kv.second.have_events)
+            for (int i = 0; i < 4; ++i) cudaEventDestroy(kv.second.ev[i]);
         cudaSetDevice(cur);
     }
     mkf_dfm::g_ws.clear();

@@ -802,16 +802,32 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         if (a.nobs) a.nobs[b] = (int64_t)nobs;
         if (a.status) a.status[b] = bad ? MKF_STATUS_NONPOSITIVE_F : 0;
     }
-    if (HO_CAPABLE && ho_mode != HO_MODE_OFF && lane == 0) a.ho_state[wid] = HO_DONE;
+    if (HO_CAPABLE && ho_mode != HO_MODE_OFF && lane == 0) {
+        a.ho_state[wid] = HO_DONE;
+        if (ho_mode == HO_MODE_HANDOFF) a.ho_tnext[wid] = T;
+    }
 }
 
 // Builds the tensor map of y viewed as [rows][row_elems] doubles (defined in filter_dfm.cu).
 int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
                       int box_rows, int box_elems);
 // Grow-only device scratch of the hand-off records, one per (device, stream); NULL when the allocation
-// fails (the caller then stays on the single-kernel path).  Defined in filter_dfm.cu.
-void *handoff_workspace(cudaStream_t stream, size_t bytes);
+// fails (the caller then stays on the single-kernel path).  Defined in filter_dfm.cu.  The transient
+// kernel leaves tnext = T for a warp it finished itself, so sum(T - tnext) counts the warp-steps done
+// after the hand-off.
+struct HandoffScratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    // the most recent three-launch call on this stream (mkf_dfm_last_profile)
+    int64_t blocks = 0, T = 0;
+    int64_t *tnext = nullptr;
+    cudaEvent_t ev[4] = {};
+    bool have_events = false, profiled = false;
+};
+HandoffScratch *handoff_scratch(cudaStream_t stream, size_t bytes);
 bool handoff_enabled();
+bool profile_enabled();
+bool profile_events(HandoffScratch *s);
 
 // one translation unit per K instantiates M = 1..8 (keeps nvcc wall time parallel)
 template <int K>

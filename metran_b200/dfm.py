@@ -47,6 +47,103 @@ class BatchedObjective:
         return list(out)
 
 
+def near_psd(A, epsilon=0):
+    """Nearest positive semi-definite matrix, the construction of BaseSolver._nearPSD
+    (solver.py:167-191): eigenvalues clipped at epsilon, rows rescaled to the original diagonal."""
+    n = A.shape[0]
+    eigval, eigvec = np.linalg.eig(A)
+    val = np.array(np.maximum(eigval, epsilon))
+    vec = np.array(eigvec)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        T = 1 / (vec ** 2 @ val.T)
+        T = np.array(np.sqrt(np.diag(np.array(T).reshape((n)))))
+        B = T @ vec * np.diag(np.array(np.sqrt(val)).reshape((n)))
+    return B @ B.T
+
+
+def batched_covariance(fun_batch, x0, epsilon=None, diff="forward", max_rounds=8):
+    """Covariance of the parameter estimates from a finite-difference Hessian, batched.
+
+    Mirror of BaseSolver._get_covariance (solver.py:65-140): the Hessian column j is the
+    difference of two forward-difference gradients (scipy ``approx_fprime`` with absolute step
+    epsilon) taken at x0 and at x0 + d_j e_j, d_j = epsilon * max(|x0_j|, 0.1) (:106-123); the
+    covariance is pinv(Hessian), repaired through the nearest PSD matrix when a variance is not
+    positive (:126-136), and epsilon grows tenfold until every variance is positive (:138).
+
+    The reference evaluates the (n+1)^2 (forward) or (2n+1)(n+1) (central) objective values one
+    at a time.  Here scipy's own ``approx_fprime`` is first run against a recording stand-in to
+    collect exactly the points it would evaluate, ``fun_batch(points[npoints, n])`` evaluates
+    them in ONE launch, and ``approx_fprime`` is run again on the cached values -- same points,
+    same difference formulas, same result as the reference's loop.
+    """
+    from scipy.optimize import approx_fprime
+
+    x0 = np.array(x0, dtype=np.float64)
+    n = x0.shape[0]
+    if epsilon is None:
+        epsilon = np.finfo(float).eps ** (1.0 / 4)
+
+    def gradient_sites():
+        sites = [x0.copy()] if diff == "forward" else []
+        for j in range(n):
+            d = epsilon * max(np.abs(x0[j]), 0.1)
+            steps = (d,) if diff == "forward" else (d, -d)
+            for step in steps:
+                xx = x0.copy()
+                xx[j] = x0[j] + step
+                sites.append(xx)
+        return sites
+
+    cov = None
+    for _ in range(max_rounds):
+        sites = gradient_sites()
+        recorded = []
+
+        def record(x):
+            recorded.append(np.array(x, dtype=np.float64))
+            return 0.0
+
+        for site in sites:
+            approx_fprime(site, record, epsilon)
+        points = np.stack(recorded)
+        uniq, inverse = np.unique(points, axis=0, return_inverse=True)
+        values = np.asarray(fun_batch(uniq), dtype=np.float64)
+        cache = {uniq[i].tobytes(): values[i] for i in range(uniq.shape[0])}
+
+        def replay(x):
+            return cache[np.array(x, dtype=np.float64).tobytes()]
+
+        grads = [approx_fprime(site, replay, epsilon) for site in sites]
+        hessian = np.zeros((n, n))
+        pos = 0
+        f0 = None
+        if diff == "forward":
+            f0 = grads[0]
+            pos = 1
+        for j in range(n):
+            d = epsilon * max(np.abs(x0[j]), 0.1)
+            if diff == "forward":
+                ff = grads[pos]
+                pos += 1
+                hessian[: j + 1, j] = (ff[: j + 1] - f0[: j + 1]) / d
+            else:
+                ff, fb = grads[pos], grads[pos + 1]
+                pos += 2
+                hessian[: j + 1, j] = (ff[: j + 1] - fb[: j + 1]) / (2 * d)
+            hessian[j, : j + 1] = hessian[: j + 1, j]
+        if not np.isnan(hessian).any():
+            cov = np.linalg.pinv(hessian)
+            if np.amin(np.diag(cov)) <= 0:
+                try:
+                    cov = np.linalg.pinv(near_psd(hessian))
+                except Exception as e:           # as the reference: keep going with a larger step
+                    logger.debug("Could not calculate 'cov': %s", e)
+            if np.amin(np.diag(cov)) > 0:
+                return cov
+        epsilon *= 10.0
+    return cov
+
+
 class DynamicFactorModel:
     """Metran's dynamic factor model at array level, evaluated on the GPU.
 
@@ -178,12 +275,22 @@ class DynamicFactorModel:
         if hasattr(result, "hess_inv"):
             pcov = result.hess_inv.todense()
             stderr = np.sqrt(np.diag(pcov))
+        if np.isnan(stderr).any():
+            # solver.py:264-269: finite-difference Hessian; all its points in one launch
+            pcov = self.get_covariance(result.x)
+            stderr = np.sqrt(np.diag(pcov))
         self.fit = result
         self.parameters = {"optimal": np.array(result.x), "stderr": stderr, "pcov": pcov,
                            "obj_func": float(result.fun), "nfev": int(result.nfev),
                            "aic": 2 * self.nstate + float(result.fun),
                            "batched_launches": None if hook is None else hook.launches}
         return bool(getattr(result, "success", True)), np.array(result.x), stderr
+
+    def get_covariance(self, p, epsilon=None, diff="forward"):
+        """Parameter covariance from the finite-difference Hessian of -2 log L at p
+        (BaseSolver._get_covariance, solver.py:65-140), every objective value of one Hessian
+        from a single batched launch."""
+        return batched_covariance(self.get_mle_batch, p, epsilon=epsilon, diff=diff)
 
     # ------------------------------------------------------------------ getters (a12)
     def _run_kalman(self, method, p):

@@ -462,6 +462,31 @@ class SPKalmanFilter:
             mle, _, _ = eng.filter_loglik(snap["y"], A, Q, H, R, x0=x0[None], P0=P0[None], flags=flags)
         return float(mle[0])
 
+    def loglik_batch(self, A, Q, H, R, warmup=1):
+        """-2 log L of the resident observations for a BATCH of matrix sets A,Q[B,n,n], H[B,m,n],
+        R[B,m] in one launch (default initial state): the thread-per-model DFM kernel when every
+        set is Metran-shaped, else the generic kernel.  Used by the batched Hessian."""
+        eng = self._device_engine()
+        if self._y_dev is None:
+            self._y_dev = eng.tensor(unpack_observations(self.observations, self.observation_indices,
+                                                         self.observation_count)[None])
+        A, Q, H, R = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, Q, H, R))
+        B, m, n = H.shape
+        y = self._y_dev[0]
+        eye = np.eye(n, dtype=bool)
+        diag = not np.any(A[:, ~eye]) and not np.any(Q[:, ~eye])
+        dfm = (diag and m <= n and eng.dfm_supported(m, n - m)
+               and np.array_equal(H[:, :, :m], np.broadcast_to(np.eye(m), (B, m, m))))
+        if dfm:
+            phi = np.ascontiguousarray(np.diagonal(A, axis1=1, axis2=2))
+            q = np.ascontiguousarray(np.diagonal(Q, axis1=1, axis2=2))
+            mle, _, _ = eng.dfm_loglik(y, phi, q, np.ascontiguousarray(H[:, :, m:]),
+                                       r=R if np.any(R) else None, warmup=warmup)
+        else:
+            flags = (_lib.FLAG_A_DIAGONAL | _lib.FLAG_Q_DIAGONAL) if diag else 0
+            mle, _, _ = eng.filter_loglik(y, A, Q, H, R, warmup=warmup, flags=flags)
+        return mle.cpu().numpy()
+
     def _filter_on_device(self, snap):
         eng = self._device_engine()
         out = _filter_device(eng, snap["y"], snap["A"], snap["Q"], snap["H"], snap["R"], snap["x0"], snap["P0"])

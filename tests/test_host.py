@@ -306,3 +306,70 @@ def test_steady_state_cases_are_sound(eng, m, k):
     import steady_state_cases as ssc
 
     ssc.check(eng, m, k, lambda t: t.cpu().numpy())
+
+
+# ---------------------------------------------------------- batched FD Hessian (solver.py:65-140)
+def _reference_style_covariance(f, x0, epsilon=None, diff="forward"):
+    """The loop of BaseSolver._get_covariance (solver.py:96-140) restated with one objective call at
+    a time -- what the batched version must reproduce."""
+    from scipy.optimize import approx_fprime
+
+    from metran_b200.dfm import near_psd
+
+    n = x0.shape[0]
+    if epsilon is None:
+        epsilon = np.finfo(float).eps ** (1.0 / 4)
+    for _ in range(8):
+        hessian = np.zeros((n, n))
+        xx = x0.copy()
+        if diff == "forward":
+            f0 = approx_fprime(x0, f, epsilon)
+        for j in range(n):
+            xx0 = xx[j]
+            d = epsilon * max(np.abs(xx0), 0.1)
+            xx[j] = xx0 + d
+            ff = approx_fprime(xx, f, epsilon)
+            if diff == "central":
+                xx[j] = xx0 - d
+                fb = approx_fprime(xx, f, epsilon)
+                hessian[: j + 1, j] = (ff[: j + 1] - fb[: j + 1]) / (2 * d)
+            else:
+                hessian[: j + 1, j] = (ff[: j + 1] - f0[: j + 1]) / d
+            hessian[j, : j + 1] = hessian[: j + 1, j]
+            xx[j] = xx0
+        cov = np.linalg.pinv(hessian)
+        if np.amin(np.diag(cov)) <= 0:
+            cov = np.linalg.pinv(near_psd(hessian))
+        if np.amin(np.diag(cov)) > 0:
+            return cov
+        epsilon *= 10.0
+    return cov
+
+
+@pytest.mark.parametrize("diff", ["forward", "central"])
+def test_batched_covariance_matches_the_reference_loop(eng, nbmodel, diff):
+    """All (n+1)^2 objective values of a Hessian from ONE batched launch, identical to the
+    one-call-at-a-time loop of the reference."""
+    from metran_b200.dfm import DynamicFactorModel
+
+    g = nbmodel
+    dfm = DynamicFactorModel(g["y"], g["factors"], engine=eng)
+    x0 = g["alpha_opt"].astype(float)
+    calls = []
+    orig = dfm.get_mle_batch
+
+    def counting(P):
+        calls.append(np.atleast_2d(P).shape[0])
+        return orig(P)
+
+    dfm.get_mle_batch = counting
+    cov = dfm.get_covariance(x0, diff=diff)
+    n = x0.size
+    assert len(calls) == 1 and calls[0] <= ((n + 1) ** 2 if diff == "forward" else (2 * n + 1) * (n + 1))
+    want = _reference_style_covariance(lambda p: float(orig(np.asarray(p)[None])[0]), x0, diff=diff)
+    np.testing.assert_allclose(cov, want, rtol=1e-9, atol=1e-12)
+    assert np.all(np.diag(cov) > 0)
+    # the reference's own stderr at this optimum came from L-BFGS-B's hess_inv; the FD Hessian must be
+    # of the same order of magnitude (loose: different estimators of the same curvature)
+    ratio = np.sqrt(np.diag(cov)) / g["stderr"]
+    assert np.all((ratio > 0.05) & (ratio < 20.0)), ratio

@@ -80,3 +80,26 @@ def test_mask_path_through_installed_engine(installed, b21):
     np.testing.assert_allclose(proj2.values[int(b21["mask_row"])], b21["masked_sim_row"], atol=1e-6)
     np.testing.assert_allclose(proj2.values[int(b21["mask_row"])],
                                [5.92966842, 0.78340608, 11.07593077], atol=1e-6)
+
+
+def test_hessian_of_the_reference_solver_is_batched(installed, b21):
+    """install() also swaps BaseSolver._get_covariance (solver.py:65-140): same numbers as the
+    reference's one-call-at-a-time loop, one kernel launch for all its points."""
+    metran, eng = installed
+    import importlib
+
+    inst = importlib.import_module("metran_b200.install")
+
+    mt = metran.Metran(_refload.load_example_series(), name="B21B0214")
+    mt.solve(report=False)
+    solver = mt.fit
+    x0 = solver.result.x.copy()
+    n0 = len(eng.lib.calls)
+    cov = solver._get_covariance(x0.copy(), solver.objfunction, solver._array_todict)
+    names = [c[0] for c in eng.lib.calls[n0:]]
+    assert names == ["mkf_dfm_loglik"], names                      # ONE launch for (n+1)^2 points
+    n1 = len(eng.lib.calls)
+    want = inst._saved["_get_covariance"](solver, x0.copy(), solver.objfunction, solver._array_todict)
+    assert len(eng.lib.calls) - n1 == (x0.size + 1) ** 2            # the reference's loop, one launch each
+    np.testing.assert_allclose(cov, want, rtol=1e-9, atol=1e-12)
+    assert np.all(np.diag(cov) > 0)

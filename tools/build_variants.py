@@ -4,15 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    "base": [],
-    # steady-state kernel (dfm_steady.cuh): tile length x ring depth, resident CTAs per SM
-    "st_2x4": ["-DMKF_ST_TT=2", "-DMKF_ST_STAGES=4"],
-    "st_2x10": ["-DMKF_ST_TT=2", "-DMKF_ST_STAGES=10"],
-    "st_4x4": ["-DMKF_ST_TT=4", "-DMKF_ST_STAGES=4"],
+    # steady-state kernel (dfm_steady.cuh): tile length x ring depth (default 2 x 8)
+    "st_6x2": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=2"],
     "st_6x3": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=3"],
-    "st_6x4_minb8": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=4", "-DMKF_ST_MINB=8"],
-    "st_2x6_minb8": ["-DMKF_ST_MINB=8"],
-    "st_2x6_minb16": ["-DMKF_ST_MINB=16"],
+    # transient kernel candidates
+    "tr_rcp3": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=2", "-DMKF_RCP3=1"],
+    "tr_check1": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=2", "-DMKF_FREEZE_EVERY_STEP=1", "-DMKF_FREEZE_NCONV=12"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}

@@ -1,7 +1,8 @@
 """Print key metrics + per-instruction stall hot spots from an .ncu-rep (build container)."""
 import csv, io, subprocess, sys, collections
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []   # one kernel of a multi-kernel report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + ksel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); d = dict(zip(rows[0], rows[2])); u = dict(zip(rows[0], rows[1]))
 for k in ["gpu__time_duration.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.max.pct_of_peak_sustained_elapsed",
           "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "launch__registers_per_thread",
@@ -11,8 +12,10 @@ for k in ["gpu__time_duration.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak
           "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
           "smsp__average_warp_latency_per_inst_issued.ratio", "dram__bytes_read.sum", "launch__grid_size"]:
     print(k, d.get(k), u.get(k))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]; data = rows[2:]; ix = {h: i for i, h in enumerate(hdr)}
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + ksel, capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]
+end = next((i for i in range(2, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))   # first (SASS) block only
+data = [r for r in rows[2:end] if len(r) >= len(hdr) - 2]; ix = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ix["# Samples"]]) for r in data)
 mx = max(int(r[ix["Instructions Executed"]]) for r in data)
 loop = [r for r in data if int(r[ix["Instructions Executed"]]) >= 0.95 * mx]
