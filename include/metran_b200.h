@@ -157,6 +157,30 @@ int mkf_dfm_loglik_alpha(int64_t B, int64_t T, int32_t m, int32_t k,
                          double *mle, int64_t *nobs, int32_t *status, void *stream);
 
 /*
+ * -2 log L on a COMPACTED time grid.  Metran forces a daily grid
+ * (metran.py:571), so irregularly sampled series are mostly steps without any observation (94.5 % of
+ * the reference's example data), for which the filter only predicts (kalmanfilter.py:335 not taken).
+ * yc[B][J][m] holds the steps with at least one observation, tidx[B][J] (int32, ascending) their
+ * original time indices; the k = tidx[j] - tidx[j-1] predicts between two of them are applied in
+ * closed form (A, Q diagonal): phi^k and q (1 - phi^2k) / (1 - phi^2).  Models with fewer than J
+ * observed steps pad with NaN rows and repeat their last index (k = 0: a no-op).  warmup / nobs
+ * semantics as mkf_filter_history, with the ORIGINAL time index.  Either alpha (with dt) or phi
+ * and q are given (the other pointers NULL); r may be NULL.  Strides of 0 share an array.
+ * Same result as mkf_dfm_loglik on the full grid up to the rounding of the closed form
+ * (<= 1e-12 relative on -2 log L; tests/test_gpu_compact.py).
+ */
+int mkf_dfm_loglik_compact(int64_t B, int64_t J, int32_t m, int32_t k,
+                           const double *yc, int64_t yc_stride,
+                           const int32_t *tidx, int64_t tidx_stride,
+                           const double *alpha, int64_t alpha_stride, double dt,
+                           const double *phi, int64_t phi_stride,
+                           const double *q, int64_t q_stride,
+                           const double *gamma, int64_t gamma_stride,
+                           const double *r, int64_t r_stride,
+                           int32_t warmup,
+                           double *mle, int64_t *nobs, int32_t *status, void *stream);
+
+/*
  * RTS smoother (kalmanfilter.py:453-474): G_t = P_f[t] A^T P_p[t+1]^-1 (solved by
  * Cholesky; the reference uses pinv), x_s[t] = x_f[t] + G_t (x_s[t+1] - x_p[t+1]),
  * P_s[t] = P_f[t] + G_t (P_s[t+1] - P_p[t+1]) G_t^T.  sm[B][T][n], sc[B][T][n][n].

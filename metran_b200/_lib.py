@@ -34,6 +34,9 @@ SIGNATURES = {
     "mkf_dfm_loglik_alpha": (ctypes.c_int,
                              [_i64, _i64, _i32, _i32, _ptr, _i64, _ptr, _i64, _dbl, _ptr, _i64, _i32]
                              + [_ptr] * 3 + [_ptr]),
+    "mkf_dfm_loglik_compact": (ctypes.c_int,
+                               [_i64, _i64, _i32, _i32, _ptr, _i64, _ptr, _i64, _ptr, _i64, _dbl]
+                               + [_ptr, _i64] * 4 + [_i32] + [_ptr] * 3 + [_ptr]),
     "mkf_smoother": (ctypes.c_int, [_i64, _i64, _i32] + [_ptr] * 4 + [_ptr, _i64, _u32]
                      + [_ptr] * 3 + [_ptr]),
     "mkf_project": (ctypes.c_int, [_i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),

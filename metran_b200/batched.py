@@ -245,6 +245,64 @@ class KalmanEngine:
         _lib.check(self.lib, rc, "mkf_dfm_loglik_alpha")
         return mle, nobs, status
 
+    # ---- compacted time grid --------------------------------------------
+    def compact_observations(self, y):
+        """Drop the time steps without any observation: y[B,T,m] | [T,m] (NaN-coded) ->
+        (yc[B,J,m] | [J,m], tidx[B,J] | [J] int32, J, observed_fraction).
+
+        Metran's daily grid (metran.py:571) leaves most steps of irregularly sampled series
+        empty (94.5 % of the reference's example data); the filter only predicts on them
+        (kalmanfilter.py:335 not taken), which mkf_dfm_loglik_compact does in closed form.
+        J is the largest observed-step count of the batch; shorter models are padded with
+        NaN rows that repeat their last time index (a no-op for the kernel)."""
+        y = self.tensor(y)
+        shared = y.dim() == 2
+        yy = y[None] if shared else y
+        B, T, m = (int(v) for v in yy.shape)
+        obs = torch.isfinite(yy) & (yy != -1e10)           # rule of set_observations (:657, :666-667)
+        anyobs = obs.any(dim=-1)
+        cnt = anyobs.sum(dim=-1)
+        J = max(int(cnt.max()) if B else 0, 1)
+        order = torch.argsort((~anyobs).to(torch.int8), dim=-1, stable=True)[:, :J]
+        valid = torch.arange(J, device=yy.device)[None, :] < cnt[:, None]
+        last = order.gather(1, (cnt - 1).clamp(min=0)[:, None])
+        last = torch.where(cnt[:, None] > 0, last, torch.full_like(last, -1))
+        tidx = torch.where(valid, order, last.expand(-1, J)).to(torch.int32).contiguous()
+        yc = yy.gather(1, order[:, :, None].expand(-1, -1, m)).contiguous()
+        yc.masked_fill_(~valid[:, :, None], float("nan"))
+        frac = float(cnt.sum()) / max(B * T, 1)
+        if shared:
+            return yc[0], tidx[0], J, frac
+        return yc, tidx, J, frac
+
+    def dfm_loglik_compact(self, yc, tidx, gamma, alpha=None, phi=None, q=None, r=None, dt=1.0, warmup=1, out=None):
+        """-2 log L of Metran-shaped models on a compacted time grid (mkf_dfm_loglik_compact):
+        yc/tidx from ``compact_observations``; either alpha[B,n] (with dt) or phi, q[B,n]."""
+        yc, gamma = self.tensor(yc), self.tensor(gamma)
+        tidx = tidx if isinstance(tidx, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(tidx))
+        tidx = tidx.to(device=self.device, dtype=torch.int32).contiguous()
+        alpha, phi, q, r = (self.tensor(v) for v in (alpha, phi, q, r))
+        if (alpha is None) == (phi is None or q is None):
+            raise ValueError("give either alpha or phi and q")
+        par = alpha if alpha is not None else phi
+        B = self._batch((yc, 2), (par, 1), (gamma, 2), (r, 1))
+        J, m = int(yc.shape[-2]), int(yc.shape[-1])
+        k = int(par.shape[-1]) - m
+        if gamma.shape[-2:] != (m, k):
+            raise ValueError("gamma must be [.., m, k] with k = n - m")
+        if tidx.shape[-1] != J or (tidx.dim() == 2) != (yc.dim() == 3):
+            raise ValueError("tidx must match yc: [B, J] with yc[B, J, m], [J] with yc[J, m]")
+        if out is None:
+            out = (self.empty(B), self.empty(B, dtype=torch.int64), self.empty(B, dtype=torch.int32))
+        mle, nobs, status = out
+        rc = self.lib.mkf_dfm_loglik_compact(
+            B, J, m, k, _ptr(yc), self._stride(yc, 2), _ptr(tidx), 0 if tidx.dim() == 1 else J,
+            _ptr(alpha), self._stride(alpha, 1), float(dt), _ptr(phi), self._stride(phi, 1),
+            _ptr(q), self._stride(q, 1), _ptr(gamma), self._stride(gamma, 2), _ptr(r), self._stride(r, 1),
+            int(warmup), _ptr(mle), _ptr(nobs), _ptr(status), self._stream())
+        _lib.check(self.lib, rc, "mkf_dfm_loglik_compact")
+        return mle, nobs, status
+
     def dfm_loglik_alpha_host(self, y_host, alpha, gamma, dt=1.0, warmup=1, chunk_models=2048):
         """Host-resident observations -> -2 log L per model, H2D overlapped with compute.
 

@@ -37,7 +37,7 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
         bool handoff = a.use_tma && handoff_enabled() && a.T >= 4 * kMinSteadySteps;
         if (handoff)
             handoff = make_y_tensor_map(&smap, a.y, shared_y ? 1 : a.B, a.T * M, shared_y ? a.T * M : a.y_stride,
-                                        shared_y ? 1 : 32, steady_tile_steps(M) * M) == MKF_OK;
+                                        shared_y ? 1 : 32, steady_tile_steps(M) * M, 256) == MKF_OK;
         if (handoff) {
             const int64_t Bp = blocks * 32;
             const size_t rec_bytes = (size_t)HO::NF * Bp * sizeof(double);
@@ -82,6 +82,7 @@ template <int M, int K>
 int launch(const DfmArgs &a, cudaStream_t stream) {
     const bool hist = a.sigma || a.detf || a.cnt || a.fm || a.fc || a.pm || a.pc;
     if (hist) return launch_r<M, K, true, true>(a, stream);
+    if (a.tidx) return launch_r<M, K, true, false>(a, stream);   // compacted grid: the build without factor-only steps
     return a.r ? launch_r<M, K, true, false>(a, stream) : launch_r<M, K, false, false>(a, stream);
 }
 

@@ -25,11 +25,16 @@
 
 namespace mkf_dfm {
 
+// Tile shape of the steady kernel, from tools/ubench_rowstream.cu (pure streaming of y with this
+// access pattern, 8 one-warp CTAs per SM, profiles/r02_rowstream.txt): the TMA engine wants few, long
+// row pieces -- 32 rows x 6 steps (240 B per row) x 3 stages streams at 6.9 TB/s with 256-byte L2
+// promotion, 2-step tiles x 8 stages only 4.1 TB/s; L2 prefetch, LDGSTS and plain LDG.128 stay
+// below 4.7 TB/s.
 #ifndef MKF_ST_TT
-#define MKF_ST_TT 2        // time steps per tile of the steady kernel (M*TT even: 16-byte rows)
+#define MKF_ST_TT 6        // time steps per tile of the steady kernel (M*TT even: 16-byte rows)
 #endif
 #ifndef MKF_ST_STAGES
-#define MKF_ST_STAGES 8    // ring depth: all stages are in flight while one tile sits in registers
+#define MKF_ST_STAGES 3    // ring depth: all stages are in flight while one tile sits in registers
 #endif
 #ifndef MKF_ST_PROXY_FENCE
 #define MKF_ST_PROXY_FENCE 1   // fence.proxy.async between a tile's LDS and the TMA refill of its stage

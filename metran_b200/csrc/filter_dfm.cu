@@ -86,7 +86,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
-                      int box_rows, int box_elems) {
+                      int box_rows, int box_elems, int l2_promotion_bytes) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return MKF_ERR_UNSUPPORTED;
     if (row_elems <= 0 || rows <= 0 || row_elems >= (1LL << 31) || rows >= (1LL << 31)) return MKF_ERR_UNSUPPORTED;  // int32 tile coordinates
@@ -96,7 +96,8 @@ int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t r
     cuuint32_t box[2] = {(cuuint32_t)box_elems, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(y), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    l2_promotion_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
     return r == CUDA_SUCCESS ? MKF_OK : MKF_ERR_UNSUPPORTED;
 }
@@ -146,6 +147,24 @@ extern "C" int mkf_dfm_loglik_alpha(int64_t B, int64_t T, int32_t m, int32_t k, 
     a.B = B; a.T = T; a.y = y; a.y_stride = y_stride;
     a.gamma = gamma; a.gamma_stride = gamma_stride;
     a.alpha = alpha; a.alpha_stride = alpha_stride; a.dt = dt; a.warmup = warmup;
+    a.mle = mle; a.nobs = nobs; a.status = status;
+    return mkf_dfm::run(m, k, a, (cudaStream_t)stream);
+}
+
+extern "C" int mkf_dfm_loglik_compact(int64_t B, int64_t J, int32_t m, int32_t k, const double *yc, int64_t yc_stride,
+                                      const int32_t *tidx, int64_t tidx_stride, const double *alpha,
+                                      int64_t alpha_stride, double dt, const double *phi, int64_t phi_stride,
+                                      const double *q, int64_t q_stride, const double *gamma, int64_t gamma_stride,
+                                      const double *r, int64_t r_stride, int32_t warmup, double *mle, int64_t *nobs,
+                                      int32_t *status, void *stream) {
+    if (!tidx || (!alpha && !(phi && q))) return MKF_ERR_BAD_ARG;
+    mkf_dfm::DfmArgs a{};
+    a.B = B; a.T = J; a.y = yc; a.y_stride = yc_stride;
+    a.tidx = tidx; a.tidx_stride = tidx_stride;
+    a.gamma = gamma; a.gamma_stride = gamma_stride; a.r = r; a.r_stride = r_stride;
+    a.alpha = alpha; a.alpha_stride = alpha_stride; a.dt = alpha ? dt : 1.0;
+    a.phi = phi; a.phi_stride = phi_stride; a.q = q; a.q_stride = q_stride;
+    a.warmup = warmup;
     a.mle = mle; a.nobs = nobs; a.status = status;
     return mkf_dfm::run(m, k, a, (cudaStream_t)stream);
 }

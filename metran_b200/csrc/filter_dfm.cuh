@@ -60,6 +60,10 @@ struct DfmArgs {
     double *sigma, *detf;
     int32_t *cnt;
     double *fm, *fc, *pm, *pc;
+    // compacted time grid (mkf_dfm_loglik_compact): y holds the observed steps only, tidx[j] is the
+    // original time index of compacted step j (ascending; padding repeats the last index).  NULL = off
+    const int32_t *tidx;
+    int64_t tidx_stride;
     // hand-off between this kernel and the steady-state kernel (dfm_steady.cuh); ho_mode 0 = off
     int ho_mode;          // HO_MODE_*
     double *ho_ws;        // records, field-major: ho_ws[field * ho_pitch + model]
@@ -268,6 +272,28 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 #define MKF_QQ(i) (GREG ? qreg[GREG ? (i) : 0] : lds_f64(cst + (i) * 32))
 #define MKF_GG(i) (GREG ? Greg[GREG ? (i) : 0] : lds_f64(cst + (N + (i)) * 32))
 
+    // Compacted time grid (only the R-capable, no-history build; never together with the factor-only
+    // step).  Between two observed steps tidx[j-1] < tidx[j] lie k - 1 steps without any observation:
+    // the reference runs k predicts (kalmanfilter.py:318-331, the update branch :335 not taken), which
+    // for diagonal A, Q have the closed form  x <- phi^k x,  P_ij <- phi_i^k phi_j^k P_ij +
+    // delta_ij q_i (1 - phi_i^2k) / (1 - phi_i^2).  phi^k = exp(k ln phi) and 1 - phi^2k = -expm1(2 k ln phi)
+    // keep the relative error at the ulp level for every k; k = 1 uses phi and q themselves.
+    constexpr bool CAN_COMPACT = HASR && !HIST;
+    const bool compact = CAN_COMPACT && a.tidx != nullptr;
+    double lnphi[CAN_COMPACT ? N : 1], cq[CAN_COMPACT ? N : 1];
+    if constexpr (CAN_COMPACT) {
+        if (compact) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                lnphi[i] = a.alpha ? -a.dt / a.alpha[bb * a.alpha_stride + i] : log(phi[i]);
+                const double den = -expm1(2.0 * lnphi[i]);          // 1 - phi^2
+                cq[i] = den > 0.0 ? MKF_QQ(i) / den : 0.0;
+            }
+        }
+    }
+    const int32_t *tix = compact ? a.tidx + bb * a.tidx_stride : nullptr;
+    int t_prev = -1, t_cur = 0;
+
     // ---- state: x0 = 0, P0 = I (kalmanfilter.py:747-750) ------------------------------
     double x[N], P[NT];
 #pragma unroll
@@ -457,7 +483,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         pend_sigma = sigma;
         pend_prod = stepprod;
         nsig += (cnt > 0) ? 1 : 0;
-        nobs += (t0 + tt >= a.warmup) ? cnt : 0;
+        nobs += ((compact ? (int64_t)t_cur : t0 + tt) >= a.warmup) ? cnt : 0;
     };
 
 #pragma unroll
@@ -486,15 +512,47 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             double sigma = 0.0, stepprod = 1.0;
             int cnt = 0;
             // ---- predict: x = phi x ; P = phi P phi + Q (kalmanfilter.py:318-331) -----
-#pragma unroll
-            for (int i = 0; i < N; ++i) x[i] *= phi[i];
-#pragma unroll
-            for (int r = 0; r < N; ++r)
-#pragma unroll
-                for (int c = r; c < N; ++c) {
-                    double v = (phi[r] * P[tri<N>(r, c)]) * phi[c];
-                    P[tri<N>(r, c)] = (r == c) ? v + MKF_QQ(r) : v;
+            bool kstep = false;
+            if constexpr (CAN_COMPACT) {
+                if (compact) {
+                    t_cur = tix[t0 + tt];
+                    kstep = !__all_sync(0xffffffffu, t_cur - t_prev == 1);
                 }
+            }
+            if (!kstep) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) x[i] *= phi[i];
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = r; c < N; ++c) {
+                        double v = (phi[r] * P[tri<N>(r, c)]) * phi[c];
+                        P[tri<N>(r, c)] = (r == c) ? v + MKF_QQ(r) : v;
+                    }
+            } else {
+                if constexpr (CAN_COMPACT) {
+                    // k = t_cur - t_prev predicts in one (k = 0 on padding steps: identity; lanes with
+                    // k = 1 inside a warp that took this branch get phi^1 and q to rounding)
+                    const double kk = (double)(t_cur - t_prev);
+                    double pk[N], qk[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        pk[i] = exp(kk * lnphi[i]);
+                        const double om = -expm1(2.0 * kk * lnphi[i]);       // 1 - phi^2k
+                        qk[i] = cq[i] > 0.0 ? cq[i] * om : kk * MKF_QQ(i);
+                    }
+#pragma unroll
+                    for (int i = 0; i < N; ++i) x[i] *= pk[i];
+#pragma unroll
+                    for (int r = 0; r < N; ++r)
+#pragma unroll
+                        for (int c = r; c < N; ++c) {
+                            double v = (pk[r] * P[tri<N>(r, c)]) * pk[c];
+                            P[tri<N>(r, c)] = (r == c) ? v + qk[r] : v;
+                        }
+                }
+            }
+            t_prev = t_cur;
             emit(a.pm, a.pc, t0 + tt);
 
             // ---- sequential scalar updates (kalmanfilter.py:341-378) -------------------
@@ -810,7 +868,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 
 // Builds the tensor map of y viewed as [rows][row_elems] doubles (defined in filter_dfm.cu).
 int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
-                      int box_rows, int box_elems);
+                      int box_rows, int box_elems, int l2_promotion_bytes = 128);
 // Grow-only device scratch of the hand-off records, one per (device, stream); NULL when the allocation
 // fails (the caller then stays on the single-kernel path).  Defined in filter_dfm.cu.  The transient
 // kernel leaves tnext = T for a warp it finished itself, so sum(T - tnext) counts the warp-steps done

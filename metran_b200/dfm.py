@@ -231,7 +231,11 @@ class DynamicFactorModel:
             raise ValueError("parameter vectors must have %d entries" % self.nstate)
         eng = self.engine
         y = self.kf._y_dev[0]
-        if self._use_dfm_kernel():
+        if self._use_dfm_kernel() and self.kf._compact is not None:
+            # sparse daily grid: observed steps only, k-step predicts in closed form
+            mle, _, _ = eng.dfm_loglik_compact(self.kf._compact[0], self.kf._compact[1], self.factors, alpha=P,
+                                               dt=self.dt, warmup=self.warmup)
+        elif self._use_dfm_kernel():
             mle, _, _ = eng.dfm_loglik_alpha(y, P, self.factors, dt=self.dt, warmup=self.warmup)
         else:
             mats = [self._get_matrices(p) for p in P]

@@ -179,6 +179,12 @@ def kalmansmoother_cuda(filtered_state_means, filtered_state_covariances, predic
     return sm[0].cpu().numpy(), sc[0].cpu().numpy()
 
 
+def torch_int32(eng, a):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(eng.device)
+
+
 class SPKalmanFilter:
     """Kalman filter class for Metran, CUDA engine (mirror of kalmanfilter.py:479-778).
 
@@ -190,7 +196,11 @@ class SPKalmanFilter:
         this package has no CPU engine.
     """
 
+    # use the compacted time grid when at most this fraction of the steps carries an observation
+    COMPACT_BELOW = 0.5
+
     def __init__(self, engine="cuda", device_engine=None):
+        self._compact = None
         self._arrays = {}
         self._lazy = None
         self._pending = None
@@ -309,6 +319,13 @@ class SPKalmanFilter:
         y = np.where(observed, values, np.nan)
         eng = self._device_engine()
         self._y_dev = eng.tensor(y[None])
+        # Compacted grid for the log-likelihood kernel: on Metran's daily grid most steps carry no
+        # observation at all; when fewer than COMPACT_BELOW of them do, objective evaluations walk
+        # the observed steps only (mkf_dfm_loglik_compact).  Host-side, once per data set.
+        self._compact = None
+        seen = np.flatnonzero(observed.any(axis=1))
+        if 0 < seen.size <= self.COMPACT_BELOW * values.shape[0]:
+            self._compact = (eng.tensor(y[seen]), torch_int32(eng, seen))
         # results of a filter run on the previous observations must not be served for these
         self._hist = None
         self._pending = None
@@ -442,7 +459,8 @@ class SPKalmanFilter:
                     A=np.array(self.transition_matrix, dtype=np.float64),
                     Q=np.array(self.transition_covariance, dtype=np.float64),
                     H=np.array(self.observation_matrix, dtype=np.float64),
-                    R=np.array(self.observation_variance, dtype=np.float64), y=self._y_dev)
+                    R=np.array(self.observation_variance, dtype=np.float64), y=self._y_dev,
+                    compact=self._compact)
 
     def _loglik_on_device(self, snap):
         """-2 log L (warmup = 1) of the snapshot: thread-per-model DFM kernel when the model is
@@ -455,7 +473,11 @@ class SPKalmanFilter:
         dfm = (flags == (_lib.FLAG_A_DIAGONAL | _lib.FLAG_Q_DIAGONAL) and m <= n
                and eng.dfm_supported(m, n - m) and np.array_equal(H[:, :m], np.eye(m))
                and not np.any(x0) and np.array_equal(P0, np.eye(n)))
-        if dfm:
+        if dfm and snap.get("compact") is not None:
+            yc, tidx = snap["compact"]
+            mle, _, _ = eng.dfm_loglik_compact(yc, tidx, H[:, m:][None].copy(), phi=np.diag(A)[None].copy(),
+                                               q=np.diag(Q)[None].copy(), r=R[None] if np.any(R) else None)
+        elif dfm:
             mle, _, _ = eng.dfm_loglik(snap["y"], np.diag(A)[None].copy(), np.diag(Q)[None].copy(),
                                        H[:, m:][None].copy(), r=R[None] if np.any(R) else None)
         else:
@@ -480,8 +502,12 @@ class SPKalmanFilter:
         if dfm:
             phi = np.ascontiguousarray(np.diagonal(A, axis1=1, axis2=2))
             q = np.ascontiguousarray(np.diagonal(Q, axis1=1, axis2=2))
-            mle, _, _ = eng.dfm_loglik(y, phi, q, np.ascontiguousarray(H[:, :, m:]),
-                                       r=R if np.any(R) else None, warmup=warmup)
+            if self._compact is not None:
+                mle, _, _ = eng.dfm_loglik_compact(self._compact[0], self._compact[1], np.ascontiguousarray(H[:, :, m:]),
+                                                   phi=phi, q=q, r=R if np.any(R) else None, warmup=warmup)
+            else:
+                mle, _, _ = eng.dfm_loglik(y, phi, q, np.ascontiguousarray(H[:, :, m:]),
+                                           r=R if np.any(R) else None, warmup=warmup)
         else:
             flags = (_lib.FLAG_A_DIAGONAL | _lib.FLAG_Q_DIAGONAL) if diag else 0
             mle, _, _ = eng.filter_loglik(y, A, Q, H, R, warmup=warmup, flags=flags)

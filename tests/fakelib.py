@@ -168,6 +168,42 @@ class FakeLib:
 
         return self._dfm(B, T, m, k, y, ys, phi_of, q_of, gamma, gs, None, 0, warmup, mle, nobs, status)
 
+    def mkf_dfm_loglik_compact(self, B, J, m, k, yc, ycs, tidx, ts, alpha, als, dt, phi, ps, q, qs, gamma, gs, r, rs,
+                               warmup, mle, nobs, status, stream):
+        """Compacted grid: re-expanded to the full daily grid and filtered by the oracle, i.e. the
+        reference's own step-by-step semantics."""
+        self.calls.append(("mkf_dfm_loglik_compact", B, J, m, k))
+        n = m + k
+        ti_all = _arr(tidx, (B if ts else 1, J), np.int32)
+        mle_o = _arr(mle, (B,)); nobs_o = _arr(nobs, (B,), np.int64); st_o = _arr(status, (B,), np.int32)
+        for b in range(B):
+            ycb = _model(yc, b, ycs, (J, m))
+            ti = ti_all[b if ts else 0].astype(np.int64)
+            T = int(ti.max()) + 1 if ti.size and ti.max() >= 0 else 1
+            yb = np.full((T, m), np.nan)
+            keep = np.concatenate([[True], np.diff(ti) > 0]) & (ti >= 0)
+            yb[ti[keep]] = ycb[keep]
+            G = _model(gamma, b, gs, (m, k)) if k else np.zeros((m, 0))
+            if _addr(alpha):
+                ph = np.exp(-dt / _model(alpha, b, als, (n,)))
+                comm = np.sum(G ** 2, axis=1)
+                qq = np.concatenate([(1 - ph[:m] ** 2) * (1 - comm), 1 - ph[m:] ** 2])
+            else:
+                ph, qq = _model(phi, b, ps, (n,)), _model(q, b, qs, (n,))
+            H = np.concatenate([np.eye(m), G], axis=1)
+            Rb = _model(r, b, rs, (m,))
+            Rb = np.zeros(m) if Rb is None else Rb
+            val, nb = ko.filter_loglik(yb, np.diag(ph), np.diag(qq), H, Rb, warmup=warmup)
+            mle_o[b] = val
+            if nobs_o is not None:
+                nobs_o[b] = nb
+            if st_o is not None:
+                st_o[b] = 0 if np.isfinite(val) else 1
+        return 0
+
+    def mkf_dfm_set_handoff(self, enabled):
+        return 1
+
     # ---- smoother / projections / reduction ---------------------------------------------
     def mkf_smoother(self, B, T, n, fm, fc, pm, pc, A, As, flags, sm, sc, status, stream):
         self.calls.append(("mkf_smoother", B, T, n))

@@ -211,7 +211,8 @@ def test_dfm_objective_and_batch(eng, b21):
     for a, key in ((A, "A_opt"), (Q, "Q_opt"), (H, "H_opt"), (R, "R_opt")):
         assert np.array_equal(a, g[key])
     if hasattr(eng.lib, "calls"):
-        assert eng.lib.calls[-1][0] == "mkf_dfm_loglik_alpha" and eng.lib.calls[-1][1] == 16
+        # 94.5 % of B21B0214's daily steps are empty: the batch walks the observed steps only
+        assert eng.lib.calls[-1][:3] == ("mkf_dfm_loglik_compact", 16, int(g["observation_count"].astype(bool).sum()))
 
 
 def test_dfm_solve_reaches_reference_optimum(eng, nbmodel):
@@ -373,3 +374,76 @@ def test_batched_covariance_matches_the_reference_loop(eng, nbmodel, diff):
     # of the same order of magnitude (loose: different estimators of the same curvature)
     ratio = np.sqrt(np.diag(cov)) / g["stderr"]
     assert np.all((ratio > 0.05) & (ratio < 20.0)), ratio
+
+
+# ------------------------------------------------------------------ compacted time grid (f4)
+def _sparse_batch(seed=0, B=7, T=300, m=4, k=2):
+    rng = np.random.default_rng(seed)
+    n = m + k
+    alpha = rng.uniform(3.0, 60.0, (B, n))
+    G = rng.uniform(0.3, 0.9, (B, m, k)) / np.sqrt(k)
+    y = rng.standard_normal((B, T, m))
+    keep = rng.random((B, T)) < rng.uniform(0.03, 0.3, (B, 1))      # ragged: different counts per model
+    y[~keep] = np.nan
+    y[rng.random(y.shape) < 0.2] = np.nan                              # partially observed days
+    y[1] = np.nan                                                      # a model without any observation
+    y[2, 0] = np.nan                                                   # first step empty
+    y[3, 17, 0] = -1e10                                                # the reference's sentinel = missing
+    y[3, 18, 1] = np.inf
+    return y, alpha, G
+
+
+def test_compact_observations_properties(eng):
+    y, alpha, G = _sparse_batch()
+    yc, tidx, J, frac = eng.compact_observations(y)
+    yc, tidx = yc.numpy(), tidx.numpy()
+    obs = np.isfinite(y) & (y != -1e10)
+    anyobs = obs.any(-1)
+    assert J == anyobs.sum(1).max() and yc.shape == (y.shape[0], J, y.shape[2]) and tidx.dtype == np.int32
+    for b in range(y.shape[0]):
+        steps = np.flatnonzero(anyobs[b])
+        c = steps.size
+        assert np.array_equal(tidx[b, :c], steps)
+        assert np.array_equal(np.isnan(yc[b, :c]), np.isnan(y[b, steps]))
+        assert np.array_equal(np.nan_to_num(yc[b, :c], nan=0.0, posinf=1.0, neginf=-1.0),
+                              np.nan_to_num(y[b, steps], nan=0.0, posinf=1.0, neginf=-1.0))
+        assert np.all(np.isnan(yc[b, c:])) and np.all(tidx[b, c:] == (steps[-1] if c else -1))
+    # shared block
+    yc1, t1, J1, _ = eng.compact_observations(y[0])
+    assert yc1.shape == (J1, y.shape[2]) and t1.shape == (J1,) and J1 == anyobs[0].sum()
+
+
+@pytest.mark.parametrize("warmup", [0, 1, 3])
+def test_compact_path_equals_full_grid(eng, warmup):
+    """Host side of the compacted grid: indices, padding, warmup / nobs on the ORIGINAL time axis."""
+    y, alpha, G = _sparse_batch(seed=1)
+    yc, tidx, J, _ = eng.compact_observations(y)
+    full = eng.dfm_loglik_alpha(y, alpha, G, warmup=warmup)
+    comp = eng.dfm_loglik_compact(yc, tidx, G, alpha=alpha, warmup=warmup)
+    keep = np.ones(y.shape[0], dtype=bool)
+    keep[1] = False                       # all-missing model: the oracle's mle is 0 - both agree on nobs
+    np.testing.assert_allclose(comp[0].numpy()[keep], full[0].numpy()[keep], rtol=0, atol=1e-9)
+    assert np.array_equal(comp[1].numpy(), full[1].numpy())
+    phi = np.exp(-1.0 / alpha)
+    q = np.concatenate([(1 - phi[:, :4] ** 2) * (1 - (G ** 2).sum(2)), 1 - phi[:, 4:] ** 2], axis=1)
+    comp2 = eng.dfm_loglik_compact(yc, tidx, G, phi=phi, q=q, warmup=warmup)
+    np.testing.assert_allclose(comp2[0].numpy()[keep], full[0].numpy()[keep], rtol=0, atol=1e-9)
+    with pytest.raises(ValueError):
+        eng.dfm_loglik_compact(yc, tidx, G, alpha=alpha, phi=phi, q=q)
+
+
+def test_spkalmanfilter_uses_compact_grid_for_sparse_data(eng, b21):
+    from metran_b200.kalmanfilter import SPKalmanFilter
+
+    g = b21
+    kf = SPKalmanFilter(device_engine=eng)
+    kf.set_observations(g["y"])
+    assert kf._compact is not None and kf._compact[0].shape[0] == int((g["observation_count"] > 0).sum())
+    kf.set_matrices(g["A_opt"], g["Q_opt"], g["H_opt"], g["R_opt"])
+    kf.run_filter()
+    assert eng.lib.calls[-1][0] == "mkf_dfm_loglik_compact"
+    assert abs(kf.get_mle() - float(g["mle_opt"])) < 1e-9
+    np.testing.assert_allclose(kf.sigmas, g["sigmas"], atol=1e-12)      # history: the full grid, as ever
+    kf2 = SPKalmanFilter(device_engine=eng)
+    kf2.set_observations(np.random.default_rng(0).standard_normal((50, 5)))   # dense data: no compaction
+    assert kf2._compact is None

@@ -45,7 +45,8 @@ def test_metran_solve_and_getters_through_installed_engine(installed, b21):
     # every objective evaluation of solve() was ONE log-likelihood kernel call; the history
     # kernel is deferred until a getter reads state arrays
     names = [c[0] for c in eng.lib.calls]
-    assert names.count("mkf_dfm_loglik") == mt.fit.nfev and "mkf_filter_history" not in names
+    # (on the compacted grid: 343 of the 6255 daily steps of B21B0214 carry an observation)
+    assert names.count("mkf_dfm_loglik_compact") == mt.fit.nfev and "mkf_filter_history" not in names
     assert abs(mt.fit.obj_func - float(b21["obj_opt"])) < 1e-6
     np.testing.assert_allclose(mt.parameters["optimal"].values.astype(float), b21["alpha_opt"], rtol=1e-4)
     sel = b21["sel"]
@@ -97,7 +98,7 @@ def test_hessian_of_the_reference_solver_is_batched(installed, b21):
     n0 = len(eng.lib.calls)
     cov = solver._get_covariance(x0.copy(), solver.objfunction, solver._array_todict)
     names = [c[0] for c in eng.lib.calls[n0:]]
-    assert names == ["mkf_dfm_loglik"], names                      # ONE launch for (n+1)^2 points
+    assert names == ["mkf_dfm_loglik_compact"], names                      # ONE launch for (n+1)^2 points
     n1 = len(eng.lib.calls)
     want = inst._saved["_get_covariance"](solver, x0.copy(), solver.objfunction, solver._array_todict)
     assert len(eng.lib.calls) - n1 == (x0.size + 1) ** 2            # the reference's loop, one launch each
