@@ -1,0 +1,116 @@
+"""Replay of the call trace of the UNMODIFIED reference facade against this package's Kalman object.
+
+tests/golden/call_trace_b21.npz (made by tests/golden/make_call_trace.py in the build container)
+holds, in order, every call ``Metran`` made on the reference's ``SPKalmanFilter`` while the
+reference's example workflow ran -- solve() (77 objective evaluations), the state / simulation /
+decomposition getters, mask_observations(), get_simulation() on the masked data, unmask -- with
+the arguments and with what the reference (numba engine) answered.  The same calls are issued
+here on ``metran_b200.SPKalmanFilter`` and every answer is compared: -2 log L to 1e-9 absolute,
+sigmas / detfs to 1e-10, states / projections to 1e-8 (BASELINE.json north_star tolerances).
+
+CPU: through the oracle-backed stand-in library (proves the harness and the host mirror).
+GPU: against the real CUDA library -- the composition "unmodified facade + CUDA engine" on the
+box where the reference itself cannot be installed.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from conftest import GOLDEN
+
+
+def _events():
+    z = np.load(os.path.join(GOLDEN, "call_trace_b21.npz"))
+    names = [str(n) for n in z["names"]]
+    fields = [dict() for _ in names]
+    for key in z.files:
+        if "/" in key:
+            i, f = key.split("/")
+            fields[int(i)][f] = z[key]
+    return list(zip(names, fields))
+
+
+def replay(eng):
+    from metran_b200.kalmanfilter import SPKalmanFilter
+
+    kf = None
+    stats = {"get_mle": 0.0, "sigmas": 0.0, "states": 0.0, "smoothed": 0.0, "proj": 0.0, "n": 0}
+
+    def upd(key, a, b):
+        stats[key] = max(stats[key], float(np.max(np.abs(np.asarray(a) - np.asarray(b)))))
+
+    for name, f in _events():
+        stats["n"] += 1
+        if name == "__init__":
+            kf = SPKalmanFilter(engine=str(f["engine"]), device_engine=eng)
+        elif name == "init_states":
+            kf.init_states()
+            assert kf.filtered_state_means is None and kf.smoothed_state_means is None
+        elif name == "set_observations":
+            kf.set_observations(pd.DataFrame(f["values"]))
+            assert np.array_equal(kf.observation_count, f["observation_count"])
+        elif name == "set_matrices":
+            kf.set_matrices(f["A"], f["Q"], f["H"], f["R"])
+        elif name in ("run_filter", "run_smoother"):
+            kf.mask = bool(f["mask"])
+            getattr(kf, name)()
+            if "sm" in f or stats["n"] % 10 == 0 or bool(f["mask"]):
+                # (reading the state arrays materialises the history: every 10th objective
+                # evaluation and every getter-driven run, as the facade itself reads them)
+                s = f["sel"]
+                upd("sigmas", kf.sigmas, f["sigmas"])
+                upd("sigmas", kf.detfs, f["detfs"])
+                upd("states", kf.filtered_state_means[s], f["fm"])
+                upd("states", kf.filtered_state_covariances[s], f["fc"])
+                upd("states", kf.predicted_state_means[s], f["pm"])
+                upd("states", kf.predicted_state_covariances[s], f["pc"])
+            if "sm" in f:
+                upd("smoothed", kf.smoothed_state_means[f["sel"]], f["sm"])
+                upd("smoothed", kf.smoothed_state_covariances[f["sel"]], f["sc"])
+        elif name == "get_mle":
+            upd("get_mle", kf.get_mle(int(f["warmup"])), f["result"])
+        elif name == "simulate":
+            means, var = kf.simulate(f["H"], method=str(f["method"]))
+            assert isinstance(means, list) and isinstance(var, list)
+            upd("proj", np.asarray(means)[f["sel"]], f["means"])
+            upd("proj", np.asarray(var)[f["sel"]], f["variances"])
+        elif name == "decompose":
+            sdf, cdf = kf.decompose(f["H"], method=str(f["method"]))
+            upd("proj", np.asarray(sdf)[f["sel"]], f["sdf"])
+            upd("proj", np.stack([np.asarray(c)[f["sel"]] for c in cdf]), f["cdf"])
+        else:
+            raise AssertionError("unknown event " + name)
+    return stats
+
+
+def _check(stats):
+    assert stats["n"] == 249
+    assert stats["get_mle"] <= 1e-9, stats
+    assert stats["sigmas"] <= 1e-10, stats
+    assert stats["states"] <= 1e-8 and stats["smoothed"] <= 1e-8 and stats["proj"] <= 1e-8, stats
+
+
+def test_replay_on_the_host_stand_in():
+    from fakelib import FakeLib
+
+    from metran_b200.batched import KalmanEngine
+
+    eng = KalmanEngine(lib=FakeLib(), device="cpu")
+    _check(replay(eng))
+    names = [c[0] for c in eng.lib.calls]
+    # every run_filter (77 objective evaluations + 3 inside run_smoother) is ONE log-likelihood call
+    # on the compacted grid; the history kernel only runs where state arrays were read
+    assert names.count("mkf_dfm_loglik_compact") == 80 and names.count("mkf_smoother") == 3
+    assert names.count("mkf_filter_history") < 20
+
+
+@pytest.mark.gpu
+def test_replay_on_the_cuda_engine():
+    from metran_b200.batched import KalmanEngine
+
+    stats = replay(KalmanEngine())
+    _check(stats)
+    print("call-trace replay on CUDA: max |d| get_mle %.2e, sigmas/detfs %.2e, states %.2e, smoothed %.2e, "
+          "projections %.2e over %d calls" % (stats["get_mle"], stats["sigmas"], stats["states"], stats["smoothed"],
+                                             stats["proj"], stats["n"]))

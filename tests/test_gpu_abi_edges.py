@@ -64,9 +64,9 @@ def test_tiny_and_ragged_shapes(eng, n, m, T):
     for warm in (0, 1):
         mle, nobs, status = eng.filter_loglik(y, A, Q, H, R, warmup=warm)
         ref = np.array([ko.filter_loglik(y[b], A[b], Q[b], H[b], R[b], warmup=warm)[0] for b in range(B)])
-        np.testing.assert_allclose(mle.cpu().numpy(), ref, rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(mle.cpu().numpy(), ref, rtol=0, atol=1e-9)
     out = eng.filter_history(y, A, Q, H, R)
-    np.testing.assert_allclose(out["mle"].cpu().numpy(), want, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(out["mle"].cpu().numpy(), want, rtol=0, atol=1e-9)
     assert np.array_equal(out["nobs"].cpu().numpy(), wobs)
     sm, sc, st = eng.smoother(out["fm"], out["fc"], out["pm"], out["pc"], A)
     for b in (0, B - 1):
@@ -114,8 +114,8 @@ def test_shared_observations_odd_row_length(eng):
     mats = [ko.dfm_matrices(a, G) for a in draws]
     A, Q, H, R = (np.stack([mm[i] for mm in mats]) for i in range(4))
     want, _ = ko.filter_loglik_batch(y, A, Q, H, R)
-    np.testing.assert_allclose(mle.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(mle.cpu().numpy(), want, rtol=0, atol=1e-9)
     # same with an even row (TMA path, single-row box)
     mle2, _, _ = eng.dfm_loglik_alpha(y[:76], draws, G)
     want2, _ = ko.filter_loglik_batch(y[:76], A, Q, H, R)
-    np.testing.assert_allclose(mle2.cpu().numpy(), want2, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(mle2.cpu().numpy(), want2, rtol=0, atol=1e-9)

@@ -49,7 +49,7 @@ def test_c1_full_batch_against_oracle(eng):
     mle, nobs, status = eng.dfm_loglik_alpha(y, a_d, g_d)
     want, wobs = _oracle_subset(y.cpu().numpy(), alpha, gamma, range(B))
     got = mle.cpu().numpy()
-    assert np.max(np.abs(got - want)) <= 1e-9 * np.maximum(1.0, np.abs(want) / 1e3).max()
+    assert np.max(np.abs(got - want)) <= 1e-9      # north_star: <= 1e-9 absolute on -2 log L
     assert np.array_equal(nobs.cpu().numpy(), wobs) and int(status.abs().sum()) == 0
     pooled = float(eng.reduce_sum(mle)[0])
     assert abs(pooled - np.sum(want)) <= 1e-12 * abs(np.sum(want))
@@ -66,10 +66,10 @@ def test_c2_solver_sweep_8192_draws(eng, b21):
     mats = [ko.dfm_matrices(draws[i], b21["factors"]) for i in pick]
     A, Q, H, R = (np.stack([mm[i] for mm in mats]) for i in range(4))
     want, _ = ko.filter_loglik_batch(b21["y"], A, Q, H, R)
-    np.testing.assert_allclose(got[pick], want, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(got[pick], want, rtol=0, atol=1e-9)
     # the golden draws of the reference are reproduced inside the big batch too
     mle2, _, _ = eng.dfm_loglik_alpha(b21["y"], np.concatenate([b21["alpha_draws"], draws[:100]]), b21["factors"])
-    np.testing.assert_allclose(mle2.cpu().numpy()[:16], b21["mle_draws"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(mle2.cpu().numpy()[:16], b21["mle_draws"], rtol=0, atol=1e-9)
 
 
 def test_c4_shard_properties(eng):
@@ -86,7 +86,7 @@ def test_c4_shard_properties(eng):
     # (1) random sub-batch against the oracle
     pick = np.sort(rng.choice(B, 48, replace=False))
     want, _ = _oracle_subset(y[torch.as_tensor(pick, device=y.device)].cpu().numpy(), alpha, gamma, pick)
-    np.testing.assert_allclose(got[pick], want, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(got[pick], want, rtol=0, atol=1e-9)
     # (2) splitting the batch gives bit-identical per-model results
     lo, _, _ = eng.dfm_loglik_alpha(y[: B // 2 + 7], a_d[: B // 2 + 7], g_d[: B // 2 + 7])
     hi, _, _ = eng.dfm_loglik_alpha(y[B // 2 + 7:], a_d[B // 2 + 7:], g_d[B // 2 + 7:])
@@ -101,7 +101,7 @@ def test_c4_shard_properties(eng):
     Tp = 2502
     pre, _, _ = eng.dfm_loglik_alpha(y[:256, :Tp].contiguous(), a_d[:256], g_d[:256])
     want_p, _ = _oracle_subset(y[:8, :Tp].cpu().numpy(), alpha, gamma, range(8))
-    np.testing.assert_allclose(pre.cpu().numpy()[:8], want_p, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(pre.cpu().numpy()[:8], want_p, rtol=0, atol=1e-9)
 
 
 def test_all_missing_series_equals_dropped_series(eng):

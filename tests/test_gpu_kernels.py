@@ -100,13 +100,13 @@ def test_metran_models_alpha_path(eng, request, name):
     alphas = np.concatenate([g["alpha_init"][None], g["alpha_opt"][None], g["alpha_draws"]])
     want = np.concatenate([[g["mle_init"]], [g["mle_opt"]], g["mle_draws"]])
     mle, nobs, status = eng.dfm_loglik_alpha(y, alphas, F)          # shared y, shared loadings
-    np.testing.assert_allclose(_np(mle), want, rtol=1e-12, atol=MLE_TOL)
+    np.testing.assert_allclose(_np(mle), want, rtol=0, atol=MLE_TOL)
     assert int(status.abs().sum()) == 0
     # generic kernel on the same models
     mats = [ko.dfm_matrices(a, F) for a in alphas]
     A, Q, H, R = (np.stack([mm[i] for mm in mats]) for i in range(4))
     mle2, _, _ = eng.filter_loglik(y, A, Q, H, R)
-    np.testing.assert_allclose(_np(mle2), want, rtol=1e-12, atol=MLE_TOL)
+    np.testing.assert_allclose(_np(mle2), want, rtol=0, atol=MLE_TOL)
 
 
 def test_b21_history_smoother_projection(eng, b21):
@@ -161,12 +161,12 @@ def test_dfm_random_batch_vs_oracle(eng, m, k, T, miss):
     R = np.zeros((B, m))
     want, wobs = ko.filter_loglik_batch(y, A, Q, H, R)
     mle, nobs, status = eng.dfm_loglik(y, phi, q, G)
-    np.testing.assert_allclose(_np(mle), want, rtol=1e-12, atol=MLE_TOL)
+    np.testing.assert_allclose(_np(mle), want, rtol=0, atol=MLE_TOL)
     assert np.array_equal(_np(nobs), wobs)
     mle_a, _, _ = eng.dfm_loglik_alpha(y, alpha, G)
-    np.testing.assert_allclose(_np(mle_a), want, rtol=1e-12, atol=MLE_TOL)
+    np.testing.assert_allclose(_np(mle_a), want, rtol=0, atol=MLE_TOL)
     mle_g, nobs_g, _ = eng.filter_loglik(y, A, Q, H, R)
-    np.testing.assert_allclose(_np(mle_g), want, rtol=1e-12, atol=MLE_TOL)
+    np.testing.assert_allclose(_np(mle_g), want, rtol=0, atol=MLE_TOL)
     assert np.array_equal(_np(nobs_g), wobs)
 
 
@@ -199,16 +199,16 @@ def test_dfm_collapse_transitions_vs_oracle(eng, m, k, T):
     for warmup in (1, 4):
         want, wobs = ko.filter_loglik_batch(y, A, Q, H, R, warmup=warmup)
         mle, nobs, status = eng.dfm_loglik(y, phi, q, G, warmup=warmup)
-        np.testing.assert_allclose(_np(mle), want, rtol=1e-12, atol=MLE_TOL)
+        np.testing.assert_allclose(_np(mle), want, rtol=0, atol=MLE_TOL)
         assert np.array_equal(_np(nobs), wobs)
         assert not _np(status).any()
         mle_a, _, _ = eng.dfm_loglik_alpha(y, alpha, G, warmup=warmup)
-        np.testing.assert_allclose(_np(mle_a), want, rtol=1e-12, atol=MLE_TOL)
+        np.testing.assert_allclose(_np(mle_a), want, rtol=0, atol=MLE_TOL)
     # R != 0 must take the ordinary path (H P != 0 after an update) and still agree
     Rn = np.full((B, m), 0.05)
     want, _ = ko.filter_loglik_batch(y, A, Q, H, Rn)
     mle_r, _, _ = eng.dfm_loglik(y, phi, q, G, r=Rn)
-    np.testing.assert_allclose(_np(mle_r), want, rtol=1e-12, atol=MLE_TOL)
+    np.testing.assert_allclose(_np(mle_r), want, rtol=0, atol=MLE_TOL)
 
 
 def test_reduce_sum_deterministic(eng):
