@@ -635,7 +635,7 @@ def main():
                              - eng.dfm_loglik_compact(yc21, ti21, f21, alpha=draws)[0]).abs().max())
                 e2 = mode_l_entry(
                     8192, int(y21.shape[0]), int(y21.shape[1]), int(f21.shape[1]), ms2, hbm_peak, fp64_peak,
-                    "configs[2]: the reference's example data (one shared observation block, 94.5 % empty days) on the "
+                    "configs[2]: the reference's example data (one shared observation block, 94.5 %% empty days) on the "
                     "compacted time grid (mkf_dfm_loglik_compact: %d observed steps of %d, k-step predicts in closed "
                     "form); value counts the original daily steps" % (J21, int(y21.shape[0])), shared_y=True)
                 e2["ms_full_grid"] = ms2_full

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const double *__restri
 }  // namespace
 
 extern "C" int mkf_reduce_sum(const double *v, int64_t count, double *out, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_reduce_sum");
     if (!out || count < 0 || (count > 0 && !v)) return MKF_ERR_BAD_ARG;
     reduce_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v, count, out);
     return mkf_host::check_launch();

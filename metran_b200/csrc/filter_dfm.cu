@@ -128,6 +128,7 @@ extern "C" int mkf_dfm_loglik(int64_t B, int64_t T, int32_t m, int32_t k, const 
                               const double *phi, int64_t phi_stride, const double *q, int64_t q_stride,
                               const double *gamma, int64_t gamma_stride, const double *r, int64_t r_stride,
                               int32_t warmup, double *mle, int64_t *nobs, int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_dfm_loglik");
     if (!phi || !q) return MKF_ERR_BAD_ARG;
     mkf_dfm::DfmArgs a{};
     a.B = B; a.T = T; a.y = y; a.y_stride = y_stride;
@@ -142,6 +143,7 @@ extern "C" int mkf_dfm_loglik_alpha(int64_t B, int64_t T, int32_t m, int32_t k, 
                                     int64_t y_stride, const double *alpha, int64_t alpha_stride, double dt,
                                     const double *gamma, int64_t gamma_stride, int32_t warmup, double *mle,
                                     int64_t *nobs, int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_dfm_loglik_alpha");
     if (!alpha) return MKF_ERR_BAD_ARG;
     mkf_dfm::DfmArgs a{};
     a.B = B; a.T = T; a.y = y; a.y_stride = y_stride;
@@ -157,6 +159,7 @@ extern "C" int mkf_dfm_loglik_compact(int64_t B, int64_t J, int32_t m, int32_t k
                                       const double *q, int64_t q_stride, const double *gamma, int64_t gamma_stride,
                                       const double *r, int64_t r_stride, int32_t warmup, double *mle, int64_t *nobs,
                                       int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_dfm_loglik_compact");
     if (!tidx || (!alpha && !(phi && q))) return MKF_ERR_BAD_ARG;
     mkf_dfm::DfmArgs a{};
     a.B = B; a.T = J; a.y = yc; a.y_stride = yc_stride;
@@ -175,6 +178,7 @@ extern "C" int mkf_dfm_filter_history(int64_t B, int64_t T, int32_t m, int32_t k
                                       int32_t warmup, double *sigma, double *detf, int32_t *cnt, double *fm,
                                       double *fc, double *pm, double *pc, double *mle, int64_t *nobs,
                                       int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_dfm_filter_history");
     if (!phi || !q || !mle) return MKF_ERR_BAD_ARG;
     if (!(sigma || detf || cnt || fm || fc || pm || pc)) return MKF_ERR_BAD_ARG;
     mkf_dfm::DfmArgs a{};

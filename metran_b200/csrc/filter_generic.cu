@@ -305,12 +305,29 @@ int launch(const FilterArgs &args0, cudaStream_t stream) {
     return mkf_host::check_launch();
 }
 
+}  // namespace
+
+#include "filter_block.cuh"
+
+namespace {
+
+#ifndef MKF_BLOCK_UPDATE
+#define MKF_BLOCK_UPDATE 1
+#endif
+
 template <bool HIST>
 int dispatch(const FilterArgs &a, cudaStream_t s) {
     if (a.n <= 4) return launch<4, HIST>(a, s);
     if (a.n <= 8) return launch<8, HIST>(a, s);
     if (a.n <= 16) return launch<16, HIST>(a, s);
-    if (a.n <= 32) return launch<32, HIST>(a, s);
+    if (a.n <= 32) {
+        // wide models with many series per step: eight series per block update (filter_block.cuh)
+        if (MKF_BLOCK_UPDATE && a.m >= 8) {
+            const int rc = launch_block<HIST>(a, s);
+            if (rc != MKF_ERR_UNSUPPORTED) return rc;
+        }
+        return launch<32, HIST>(a, s);
+    }
     return MKF_ERR_UNSUPPORTED;
 }
 
@@ -332,6 +349,7 @@ extern "C" int mkf_filter_history(int64_t B, int64_t T, int32_t n, int32_t m, co
                                   int32_t warmup, uint32_t flags, double *sigma, double *detf, int32_t *cnt,
                                   double *fm, double *fc, double *pm, double *pc, double *mle, int64_t *nobs,
                                   int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_filter_history");
     int rc = validate(B, T, n, m, y, A, Q, H, R);
     if (rc != MKF_OK) return rc;
     if (B == 0) return MKF_OK;
@@ -352,6 +370,7 @@ extern "C" int mkf_filter_loglik(int64_t B, int64_t T, int32_t n, int32_t m, con
                                  const double *x0, int64_t x0_stride, const double *P0, int64_t P0_stride,
                                  int32_t warmup, uint32_t flags, double *mle, int64_t *nobs, int32_t *status,
                                  void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_filter_loglik");
     int rc = validate(B, T, n, m, y, A, Q, H, R);
     if (rc != MKF_OK) return rc;
     if (!mle) return MKF_ERR_BAD_ARG;

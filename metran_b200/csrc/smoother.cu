@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(128) project_kernel(int64_t B, int64_t T, int 
 extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, const double *fc,
                             const double *pm, const double *pc, const double *A, int64_t A_stride,
                             uint32_t flags, double *sm, double *sc, int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_smoother");
     if (B < 0 || T < 0 || n <= 0) return MKF_ERR_BAD_ARG;
     if (!fm || !fc || !pm || !pc || !A || !sm || !sc) return MKF_ERR_BAD_ARG;
     if (n > 32) return MKF_ERR_UNSUPPORTED;
@@ -337,6 +338,7 @@ extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, c
 extern "C" int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p, const double *means,
                            const double *covs, const double *Hp, int64_t Hp_stride, double *means_out,
                            double *var_out, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_project");
     if (B < 0 || T < 0 || n <= 0 || p <= 0 || !means || !Hp) return MKF_ERR_BAD_ARG;
     if (var_out && !covs) return MKF_ERR_BAD_ARG;
     if (n > 64) return MKF_ERR_UNSUPPORTED;

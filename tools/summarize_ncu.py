@@ -43,6 +43,9 @@ def main():
     hdr, units = rows[0], rows[1]
     out = []
     traffic = None
+    total_traffic = 0.0
+    pipe_weighted = 0.0
+    dur_total = 0.0
     for vals in rows[2:]:
         d = dict(zip(hdr, vals))
         u = dict(zip(hdr, units))
@@ -57,17 +60,22 @@ def main():
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}[un]
 
         traffic = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-    with open("profiles/%s_ncu_full_summary.json" % tag, "w") as fh:
-        json.dump({"source": os.path.basename(rep), "command": "ncu --set full --clock-control none --import-source on "
-                   "-k regex:dfm_loglik_kernel python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu",
-                   "workload_B_T_m_k": wl, "launches": out}, fh, indent=1)
-    with open("profiles/ncu_traffic.json", "w") as fh:
-        pipe = None
+        total_traffic += traffic
         try:
-            pipe = float(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"])
+            dur = float(d["gpu__time_duration.sum"].replace(",", ""))
+            dur_total += dur
+            pipe_weighted += dur * float(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"])
         except Exception:
             pass
-        json.dump({"workload": wl, "dram_bytes_per_launch": traffic, "fp64_pipe_active_pct": pipe,
+    with open("profiles/%s_ncu_full_summary.json" % tag, "w") as fh:
+        json.dump({"source": os.path.basename(rep), "command": "ncu --set full --clock-control none --import-source on "
+                   "-k regex:dfm_ -s 9 -c 3 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-other",
+                   "workload_B_T_m_k": wl, "launches": out}, fh, indent=1)
+    with open("profiles/ncu_traffic.json", "w") as fh:
+        pipe = pipe_weighted / dur_total if dur_total > 0 else None
+        # one step of the hot path = all captured launches (transient + steady + resume kernels)
+        json.dump({"workload": wl, "dram_bytes_per_launch": total_traffic, "fp64_pipe_active_pct": pipe,
+                   "launches_summed": len(out),
                    "from": "profiles/%s_ncu_full_summary.json" % tag}, fh)
     # launch list: per-kernel totals and shares
     tot = {}
