@@ -1,4 +1,5 @@
-// Block form of the sequential-processing update for wide models (16 < n <= 32), one warp per model.
+// Block form of the sequential-processing update for wide models (16 < n <= 32): one CTA of four
+// warps per model.
 //
 // Reference: seqkalmanfilter, metran/kalmanfilter.py:341-378 -- per observed series i
 //   v_i = y_i - h_i.x,  d_i = P h_i,  f_i = h_i.d_i + r_i,  k_i = d_i / f_i,
@@ -14,37 +15,50 @@
 //   U = D L^-T                                -- column i of U is the reference's d_i
 //   x <- x + U F^-1 w,   P <- P - U F^-1 U^T,   sigma += sum w_i^2 / f_i,   detf += sum log f_i
 // Same numbers as eight sequential updates up to rounding (the elimination performs the same
-// subtractions in a different association).  Per block the lanes exchange data twice (one
-// transpose-reduction of the 36 + 8 lane products of S and v0, one broadcast of the 8 gain
-// columns) instead of 24 times, and the 2 x 256 FMAs per lane of D and of the rank-8 update are
-// independent instruction streams.  Fewer than 8 observed series left: the block is padded with
+// subtractions in a different association).
+//
+// Mapping: thread (w, l), w = warp 0..3, l = lane: row l of P, columns [8w, 8w + 8) in registers;
+// x_l replicated in the four warps.  Per block
+//   1. partial D over the thread's 8 columns (64 FMA), to shared memory            -- barrier A
+//   2. D (row l) = sum of the four partials; warp w transpose-reduces 16 of the 64 lane products
+//      (36 of S, 8 of H_b x, padding) over its lanes and publishes the totals      -- barrier B
+//   3. every thread factorises S redundantly (8 pivots; the only sequential part), forms its
+//      row of U, the innovations w and the gain columns; the warp that owns rows [8w, 8w + 8) as
+//      COLUMNS of the other threads' update publishes them                          -- barrier C
+//   4. rank-8 update of the thread's 8 covariance entries (64 FMA).
+// The small exchange buffers are double buffered by block parity, so three barriers per block are
+// all the synchronisation there is.  Fewer than 8 observed series left: the block is padded with
 // null series (h = 0, r = 1, y = 0: f = 1, v = 0, no effect).
 #pragma once
 
 namespace {
 
-// Sum over the 32 lanes of 64 per-lane values with 62 shuffles (recursive halving): afterwards lane
-// l holds the totals of entries 2l and 2l + 1 in v[0], v[1].
-__device__ __forceinline__ void transpose_reduce64(double (&v)[64], int lane) {
+// Sum over the 32 lanes of 16 per-lane values with 16 shuffles: four halving steps (offsets 16..2)
+// leave one value per lane, a final exchange with the neighbour completes it.  Afterwards lanes 2e
+// and 2e + 1 both hold the total of entry e in v[0].
+__device__ __forceinline__ void transpose_reduce16(double (&v)[16], int lane) {
 #pragma unroll
-    for (int half = 32, off = 16; half >= 2; half >>= 1, off >>= 1) {
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
         const bool upper = (lane & off) != 0;
 #pragma unroll
         for (int e = 0; e < half; ++e) {
-            // keep the half that matches this lane's bit, send the other one to the partner
             const double keep = upper ? v[e + half] : v[e];
             const double send = upper ? v[e] : v[e + half];
             v[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
     }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+constexpr int kBlkThreads = 128;
+
 template <bool HIST>
-__global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
-    constexpr int NP = 32, BS = 8, NS = BS * (BS + 1) / 2;
+__global__ void __launch_bounds__(kBlkThreads, 2) filter_block_kernel(const FilterArgs a) {
+    constexpr int NP = 32, BS = 8, NS = BS * (BS + 1) / 2, CW = 8;   // CW: columns per warp
     extern __shared__ __align__(16) double smem[];
     const int n = a.n, m = a.m;
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c0 = w * CW;
     const int64_t b = blockIdx.x;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
     const bool diagQ = a.flags & MKF_FLAG_Q_DIAGONAL;
@@ -57,8 +71,9 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
     double *sa = sm;                      sm += NP;
     double *sx = sm;                      sm += NP;
     double *sy = sm;                      sm += 2 * ytile;
-    double *sG = sm;                      sm += NP * BS;                  // gain columns [row][series]
-    double *sS = sm;                      sm += 64;                       // reduced S (upper) and v0
+    double *sDp = sm;                     sm += 2 * 4 * BS * NP;          // partial D [parity][warp][series][row]
+    double *sG = sm;                      sm += 2 * NP * BS;              // gain columns [parity][row][series]
+    double *sS = sm;                      sm += 2 * 64;                   // reduced S (upper) and H_b x [parity][64]
     double *sYo = sm;                     sm += round_up2(m + BS);        // observed values of the step, compacted
     int *sIdx = reinterpret_cast<int *>(sm); sm += round_up2((m + BS + 1) / 2);
     double *sA = sm;                      if (!diagA) sm += NP * (NP + 1) + 1;
@@ -69,31 +84,32 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
     const double *Qb = a.Q + b * a.Q_stride;
     const double *Hb = a.H + b * a.H_stride;
     const double *Rb = a.R + b * a.R_stride;
-    for (int i = r; i < (m + 1) * NP; i += NP) {
+    for (int i = threadIdx.x; i < (m + 1) * NP; i += kBlkThreads) {
         const int j = i / NP, c = i % NP;
         sH[i] = (j < m && c < n) ? Hb[j * n + c] : 0.0;
     }
-    for (int i = r; i <= m; i += NP) sR[i] = (i < m) ? Rb[i] : 1.0;
+    for (int i = threadIdx.x; i <= m; i += kBlkThreads) sR[i] = (i < m) ? Rb[i] : 1.0;
     const double a_r = (r < n) ? Ab[r * n + r] : 0.0;
-    sa[r] = a_r;
+    if (w == 0) sa[r] = a_r;
     if (!diagA)
-        for (int i = r; i < NP * NP; i += NP) {
+        for (int i = threadIdx.x; i < NP * NP; i += kBlkThreads) {
             const int rr = i / NP, c = i % NP;
             sA[rr * (NP + 1) + c] = (rr < n && c < n) ? Ab[rr * n + c] : 0.0;
         }
     if (!diagQ)
-        for (int i = r; i < NP * NP; i += NP) {
+        for (int i = threadIdx.x; i < NP * NP; i += kBlkThreads) {
             const int rr = i / NP, c = i % NP;
             sQ[rr * (NP + 1) + c] = (rr < n && c < n) ? Qb[rr * n + c] : 0.0;
         }
     const double q_r = (r < n) ? Qb[r * n + r] : 0.0;
 
-    double x = (a.x0 && r < n) ? a.x0[b * a.x0_stride + r] : 0.0;
-    double P[NP];
+    double x = (a.x0 && r < n) ? a.x0[b * a.x0_stride + r] : 0.0;     // replicated in the four warps
+    double P[CW];                                                     // P[r][c0 + c]
 #pragma unroll
-    for (int c = 0; c < NP; ++c) {
+    for (int c = 0; c < CW; ++c) {
+        const int cc = c0 + c;
         double v = 0.0;
-        if (r < n && c < n) v = a.P0 ? a.P0[b * a.P0_stride + r * n + c] : (r == c ? 1.0 : 0.0);
+        if (r < n && cc < n) v = a.P0 ? a.P0[b * a.P0_stride + r * n + cc] : (r == cc ? 1.0 : 0.0);
         P[c] = v;
     }
 
@@ -109,19 +125,20 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
             const int cntd = (int)min((int64_t)TT, T - t0) * m;
             const double *src = yb + t0 * m;
             double *dst = sy + (tile & 1) * ytile;
-            for (int i = r; i < cntd; i += NP) cp_async8(dst + i, src + i);
+            for (int i = threadIdx.x; i < cntd; i += kBlkThreads) cp_async8(dst + i, src + i);
         }
         cp_async_commit();
     };
     issue_tile(0);
     const int64_t hist_base = b * T;
-    __syncwarp();
+    __syncthreads();
 
+    int par = 0;       // parity of the exchange buffers
     for (int64_t tile = 0; tile < ntiles; ++tile) {
-        __syncwarp();
+        __syncthreads();
         issue_tile(tile + 1);
         cp_async_wait<1>();
-        __syncwarp();
+        __syncthreads();
         const double *ys = sy + (tile & 1) * ytile;
         const int64_t t0 = tile * TT;
         const int steps = (int)min((int64_t)TT, T - t0);
@@ -131,34 +148,35 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
             if (diagA) {
                 x = a_r * x;
             } else {
-                sx[r] = x;
-                __syncwarp();
+                if (w == 0) sx[r] = x;
+                __syncthreads();
                 double s = 0.0;
 #pragma unroll
                 for (int c = 0; c < NP; ++c) s = fma(sA[r * (NP + 1) + c], sx[c], s);
-                __syncwarp();
+                __syncthreads();
                 x = s;
             }
 #pragma unroll
-            for (int c = 0; c < NP; c += 2) {
-                const double2 ac = *reinterpret_cast<const double2 *>(sa + c);
+            for (int c = 0; c < CW; c += 2) {
+                const double2 ac = *reinterpret_cast<const double2 *>(sa + c0 + c);
                 const double v0 = (a_r * P[c]) * ac.x;
                 const double v1 = (a_r * P[c + 1]) * ac.y;
                 if (diagQ) {
-                    P[c] = (c == r) ? v0 + q_r : v0;
-                    P[c + 1] = (c + 1 == r) ? v1 + q_r : v1;
+                    P[c] = (c0 + c == r) ? v0 + q_r : v0;
+                    P[c + 1] = (c0 + c + 1 == r) ? v1 + q_r : v1;
                 } else {
-                    P[c] = v0 + sQ[r * (NP + 1) + c];
-                    P[c + 1] = v1 + sQ[r * (NP + 1) + c + 1];
+                    P[c] = v0 + sQ[r * (NP + 1) + c0 + c];
+                    P[c + 1] = v1 + sQ[r * (NP + 1) + c0 + c + 1];
                 }
             }
             if (HIST && r < n) {
-                if (a.pm) a.pm[(hist_base + t) * n + r] = x;
+                if (a.pm && w == 0) a.pm[(hist_base + t) * n + r] = x;
                 if (a.pc) {
-                    double *dst = a.pc + (hist_base + t) * n * n + r;
+                    // row r, columns c0..c0+7 (P is symmetric to rounding, as the reference's own)
+                    double *dst = a.pc + (hist_base + t) * n * n + (int64_t)r * n + c0;
 #pragma unroll
-                    for (int c = 0; c < NP; ++c)
-                        if (c < n) dst[(int64_t)c * n] = P[c];
+                    for (int c = 0; c < CW; ++c)
+                        if (c0 + c < n) dst[c] = P[c];
                 }
             }
 
@@ -169,22 +187,22 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
                 const double yv = (jj < m) ? ys[tt * m + jj] : nan("");
                 const bool ob = is_observed(yv);
                 const unsigned bal = __ballot_sync(0xffffffffu, ob);
-                if (ob) {
+                if (ob && w == 0) {
                     const int pos = cnt + __popc(bal & ((1u << r) - 1u));
                     sIdx[pos] = jj;
                     sYo[pos] = yv;
                 }
                 cnt += __popc(bal);
             }
-            if (r < BS) {          // padding of the last block: the null series
+            if (w == 0 && r < BS) {          // padding of the last block: the null series
                 sIdx[cnt + r] = m;
                 sYo[cnt + r] = 0.0;
             }
-            __syncwarp();
+            __syncthreads();
 
             double sigma = 0.0, fman = 1.0;
             int fexp = 0;
-            for (int blk = 0; blk < cnt; blk += BS) {
+            for (int blk = 0; blk < cnt; blk += BS, par ^= 1) {
                 const double *hrow[BS];
                 double rr[BS];
 #pragma unroll
@@ -193,69 +211,94 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
                     hrow[i] = sH + j * NP;
                     rr[i] = sR[j];
                 }
-                // D = P H_b^T (this lane: row r), from the covariance before the block
-                double D[BS];
+                // 1. partial D over this thread's columns
+                double *dp = sDp + (size_t)par * 4 * BS * NP;
+                {
+                    double Dp[BS];
 #pragma unroll
-                for (int i = 0; i < BS; ++i) D[i] = 0.0;
+                    for (int i = 0; i < BS; ++i) Dp[i] = 0.0;
 #pragma unroll
-                for (int c = 0; c < NP; c += 2) {
+                    for (int c = 0; c < CW; c += 2) {
 #pragma unroll
-                    for (int i = 0; i < BS; ++i) {
-                        const double2 h = *reinterpret_cast<const double2 *>(hrow[i] + c);
-                        D[i] = fma(P[c], h.x, D[i]);
-                        D[i] = fma(P[c + 1], h.y, D[i]);
+                        for (int i = 0; i < BS; ++i) {
+                            const double2 h = *reinterpret_cast<const double2 *>(hrow[i] + c0 + c);
+                            Dp[i] = fma(P[c], h.x, Dp[i]);
+                            Dp[i] = fma(P[c + 1], h.y, Dp[i]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < BS; ++i) dp[(w * BS + i) * NP + r] = Dp[i];
+                }
+                __syncthreads();                                                    // barrier A
+                // 2. D (row r); lane products of S = H_b D and of H_b x, 16 entries per warp
+                double D[BS], hr[BS];
+#pragma unroll
+                for (int i = 0; i < BS; ++i) {
+                    D[i] = (dp[(0 * BS + i) * NP + r] + dp[(1 * BS + i) * NP + r]) +
+                           (dp[(2 * BS + i) * NP + r] + dp[(3 * BS + i) * NP + r]);
+                    hr[i] = hrow[i][r];
+                }
+                double *ss = sS + par * 64;
+                {
+                    // entry e of the 64: e < 36: S(i, l) in row-major upper order; 36..43: (H_b x)_i
+                    double prod[48];
+                    {
+                        int e = 0;
+#pragma unroll
+                        for (int i = 0; i < BS; ++i)
+#pragma unroll
+                            for (int l = i; l < BS; ++l) prod[e++] = hr[i] * D[l];
+#pragma unroll
+                        for (int i = 0; i < BS; ++i) prod[NS + i] = hr[i] * x;
+#pragma unroll
+                        for (int i = NS + BS; i < 48; ++i) prod[i] = 0.0;
+                    }
+                    double red[16];
+                    if (w == 0) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) red[e] = prod[e];
+                    } else if (w == 1) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) red[e] = prod[16 + e];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) red[e] = prod[32 + e];
+                    }
+                    if (w < 3) {
+                        transpose_reduce16(red, r);
+                        if ((r & 1) == 0) ss[w * 16 + (r >> 1)] = red[0];
                     }
                 }
-                // lane products of S = H_b D (upper triangle) and of H_b x, summed over the lanes
-                double red[64];
-                double hr[BS];
-#pragma unroll
-                for (int i = 0; i < BS; ++i) hr[i] = hrow[i][r];
+                __syncthreads();                                                    // barrier B
+                // 3. every thread factorises S = L F L^T redundantly (8 pivots: the innovation variances)
+                double S[NS], wv[BS];
                 {
                     int e = 0;
 #pragma unroll
                     for (int i = 0; i < BS; ++i)
 #pragma unroll
-                        for (int l = i; l < BS; ++l) red[e++] = hr[i] * D[l];
+                        for (int l = i; l < BS; ++l, ++e) S[e] = ss[e] + ((l == i) ? rr[i] : 0.0);
 #pragma unroll
-                    for (int i = 0; i < BS; ++i) red[NS + i] = hr[i] * x;
-#pragma unroll
-                    for (int i = NS + BS; i < 64; ++i) red[i] = 0.0;
+                    for (int i = 0; i < BS; ++i) wv[i] = sYo[blk + i] - ss[NS + i];
                 }
-                transpose_reduce64(red, r);
-                *reinterpret_cast<double2 *>(sS + 2 * r) = make_double2(red[0], red[1]);
-                __syncwarp();
-                // every lane factorises S = L F L^T redundantly (8 pivots: the innovation variances)
-                double S[NS], w[BS];
-                {
-                    int e = 0;
-#pragma unroll
-                    for (int i = 0; i < BS; ++i)
-#pragma unroll
-                        for (int l = i; l < BS; ++l, ++e) S[e] = sS[e] + ((l == i) ? rr[i] : 0.0);
-#pragma unroll
-                    for (int i = 0; i < BS; ++i) w[i] = sYo[blk + i] - sS[NS + i];
-                }
-                __syncwarp();          // sS may be rewritten by the next block
                 auto tri8 = [](int i, int l) { return i * BS - (i * (i - 1)) / 2 + (l - i); };
-                double U[BS], gw = 0.0;
+                double U[BS], G[BS], gw = 0.0;
 #pragma unroll
                 for (int i = 0; i < BS; ++i) U[i] = D[i];
-                double G[BS];
 #pragma unroll
                 for (int i = 0; i < BS; ++i) {
                     const double f = S[tri8(i, i)];
                     const bool badf = f_is_bad(f);
                     const double rf = badf ? nan("") : rcp_nr(f);
                     if (badf) status |= MKF_STATUS_NONPOSITIVE_F;
-                    sigma = fma(w[i] * w[i], rf, sigma);
+                    sigma = fma(wv[i] * wv[i], rf, sigma);
                     fman *= f;
                     G[i] = U[i] * rf;                          // gain column i, row r
-                    gw = fma(G[i], w[i], gw);
+                    gw = fma(G[i], wv[i], gw);
 #pragma unroll
                     for (int l = i + 1; l < BS; ++l) {
                         const double mlt = S[tri8(i, l)] * rf;
-                        w[l] = fma(-mlt, w[i], w[l]);
+                        wv[l] = fma(-mlt, wv[i], wv[l]);
                         U[l] = fma(-mlt, U[i], U[l]);
 #pragma unroll
                         for (int l2 = l; l2 < BS; ++l2) S[tri8(l, l2)] = fma(-mlt, S[tri8(i, l2)], S[tri8(l, l2)]);
@@ -268,22 +311,25 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
                     fman = __hiloint2double(hi - (ex << 20), __double2loint(fman));
                 }
                 x += gw;
-                // P <- P - U G^T: gain columns of all rows through shared memory ([row][series])
+                // gain columns of all rows ([row][series]); rows are identical in the four warps
+                double *sg = sG + par * NP * BS;
+                if (w == (r >> 3)) {
 #pragma unroll
-                for (int i = 0; i < BS; i += 2) *reinterpret_cast<double2 *>(sG + r * BS + i) = make_double2(G[i], G[i + 1]);
-                __syncwarp();
+                    for (int i = 0; i < BS; i += 2) *reinterpret_cast<double2 *>(sg + r * BS + i) = make_double2(G[i], G[i + 1]);
+                }
+                __syncthreads();                                                    // barrier C
+                // 4. P[r][c0 + c] -= sum_i U[r][i] G[c0 + c][i]
 #pragma unroll
-                for (int c = 0; c < NP; ++c) {
+                for (int c = 0; c < CW; ++c) {
                     double acc = P[c];
 #pragma unroll
                     for (int i = 0; i < BS; i += 2) {
-                        const double2 g = *reinterpret_cast<const double2 *>(sG + c * BS + i);
+                        const double2 g = *reinterpret_cast<const double2 *>(sg + (c0 + c) * BS + i);
                         acc = fma(-U[i], g.x, acc);
                         acc = fma(-U[i + 1], g.y, acc);
                     }
                     P[c] = acc;
                 }
-                __syncwarp();
             }
             const double detf = (cnt > 0) ? log(fman) + (double)fexp * kLn2 : 0.0;
             if (cnt > 0) {
@@ -295,25 +341,26 @@ __global__ void __launch_bounds__(32) filter_block_kernel(const FilterArgs a) {
             }
             if (t >= a.warmup) nobs += cnt;
             if (HIST) {
-                if (r == 0) {
+                if (threadIdx.x == 0) {
                     if (a.sigma) a.sigma[hist_base + t] = sigma;
                     if (a.detf) a.detf[hist_base + t] = detf;
                     if (a.cnt) a.cnt[hist_base + t] = cnt;
                 }
                 if (r < n) {
-                    if (a.fm) a.fm[(hist_base + t) * n + r] = x;
+                    if (a.fm && w == 0) a.fm[(hist_base + t) * n + r] = x;
                     if (a.fc) {
-                        double *dst = a.fc + (hist_base + t) * n * n + r;
+                        double *dst = a.fc + (hist_base + t) * n * n + (int64_t)r * n + c0;
 #pragma unroll
-                        for (int c = 0; c < NP; ++c)
-                            if (c < n) dst[(int64_t)c * n] = P[c];
+                        for (int c = 0; c < CW; ++c)
+                            if (c0 + c < n) dst[c] = P[c];
                     }
                 }
             }
+            __syncthreads();      // sIdx / sYo are rewritten by the next step
         }
     }
     cp_async_wait<0>();
-    if (r == 0) {
+    if (threadIdx.x == 0) {
         if (a.mle) a.mle[b] = (double)nobs * kLog2Pi + sum_detf.value() + sum_sigma.value();
         if (a.nobs) a.nobs[b] = nobs;
         if (a.status) a.status[b] = status;
@@ -331,8 +378,8 @@ int launch_block(const FilterArgs &args0, cudaStream_t stream) {
     if (TT > 32) TT = 32;
     if ((int64_t)TT > a.T && a.T > 0) TT = (int)a.T;
     a.tile_steps = TT;
-    size_t per = (size_t)(a.m + 1) * NP + round_up2(a.m + 1) + NP + NP + 2 * round_up2(TT * a.m) + NP * BS + 64 +
-                 round_up2(a.m + BS) + round_up2((a.m + BS + 1) / 2);
+    size_t per = (size_t)(a.m + 1) * NP + round_up2(a.m + 1) + NP + NP + 2 * round_up2(TT * a.m) + 2 * 4 * BS * NP +
+                 2 * NP * BS + 2 * 64 + round_up2(a.m + BS) + round_up2((a.m + BS + 1) / 2);
     if (!diagA) per += NP * (NP + 1) + 1;
     if (!diagQ) per += NP * (NP + 1) + 1;
     const size_t smem = (per + 2) * sizeof(double);
@@ -343,7 +390,7 @@ int launch_block(const FilterArgs &args0, cudaStream_t stream) {
         mkf_host::set_cuda_error(e);
         return MKF_ERR_CUDA;
     }
-    kern<<<(unsigned)a.B, 32, smem, stream>>>(a);
+    kern<<<(unsigned)a.B, kBlkThreads, smem, stream>>>(a);
     return mkf_host::check_launch();
 }
 

@@ -279,6 +279,12 @@ int launch_smoother(SmootherArgs a, cudaStream_t stream) {
     return mkf_host::check_launch();
 }
 
+}  // namespace
+
+#include "smoother_wide.cuh"
+
+namespace {
+
 // ---- projections ---------------------------------------------------------------------
 // one warp per (model, time step): stage x_t and P_t in shared memory, lane i computes
 // output series i (strided when p > 32).
@@ -332,6 +338,10 @@ extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, c
     if (n <= 4) return launch_smoother<4>(a, s);
     if (n <= 8) return launch_smoother<8>(a, s);
     if (n <= 16) return launch_smoother<16>(a, s);
+#ifndef MKF_SMOOTHER_WIDE
+#define MKF_SMOOTHER_WIDE 1
+#endif
+    if (MKF_SMOOTHER_WIDE) return launch_smoother_wide(a, s);      // four warps per model (smoother_wide.cuh)
     return launch_smoother<32>(a, s);
 }
 
