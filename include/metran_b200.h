@@ -191,6 +191,21 @@ int mkf_smoother(int64_t B, int64_t T, int32_t n,
                  double *sm, double *sc, int32_t *status, void *stream);
 
 /*
+ * mkf_smoother with the projections of SPKalmanFilter.simulate (kalmanfilter.py:596-602) fused into
+ * its epilogue: while the smoothed covariance of a step is still on chip,
+ *   proj_mean[B][T][p] = Hp x_s[t],  proj_var[B][T][p] = max(diag(Hp P_s[t] Hp^T), 0),
+ *   state_var[B][T][n] = diag(P_s[t])  (may be NULL)
+ * are written, so no consumer has to read sc[B][T][n][n] back; sc itself may be NULL (then the
+ * smoothed covariances are not materialised at all).  Hp[B][p][n], stride 0 = shared.
+ */
+int mkf_smoother_project(int64_t B, int64_t T, int32_t n,
+                         const double *fm, const double *fc, const double *pm, const double *pc,
+                         const double *A, int64_t A_stride, uint32_t flags,
+                         int32_t p, const double *Hp, int64_t Hp_stride,
+                         double *sm, double *sc, double *proj_mean, double *proj_var, double *state_var,
+                         int32_t *status, void *stream);
+
+/*
  * Projection of state moments (kalmanfilter.py:596-602): means_out[B][T][p] = Hp x_t,
  * var_out[B][T][p] = max(diag(Hp P_t Hp^T), 0); Hp[B][p][n].
  */

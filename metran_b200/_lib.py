@@ -39,6 +39,8 @@ SIGNATURES = {
                                + [_ptr, _i64] * 4 + [_i32] + [_ptr] * 3 + [_ptr]),
     "mkf_smoother": (ctypes.c_int, [_i64, _i64, _i32] + [_ptr] * 4 + [_ptr, _i64, _u32]
                      + [_ptr] * 3 + [_ptr]),
+    "mkf_smoother_project": (ctypes.c_int, [_i64, _i64, _i32] + [_ptr] * 4 + [_ptr, _i64, _u32]
+                             + [_i32, _ptr, _i64] + [_ptr] * 6 + [_ptr]),
     "mkf_project": (ctypes.c_int, [_i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "mkf_dfm_set_handoff": (ctypes.c_int, [ctypes.c_int]),
     "mkf_release_workspaces": (None, []),

@@ -158,6 +158,29 @@ class KalmanEngine:
         _lib.check(self.lib, rc, "mkf_smoother")
         return sm, sc, status
 
+    def smoother_project(self, fm, fc, pm, pc, A, Hp, flags=None, covariances=True, state_variances=True):
+        """RTS smoother with the projections fused into its epilogue (mkf_smoother_project): returns a
+        dict sm[B,T,n], sc[B,T,n,n] | None, proj_mean[B,T,p], proj_var[B,T,p], state_var[B,T,n] | None,
+        status[B].  Nobody has to read the [T,n,n] covariances back to project them."""
+        fm, fc, pm, pc, A, Hp = (self.tensor(v) for v in (fm, fc, pm, pc, A, Hp))
+        if fm.dim() == 2:
+            fm, fc, pm, pc = fm[None], fc[None], pm[None], pc[None]
+        B, T, n = (int(s) for s in fm.shape)
+        p = int(Hp.shape[-2])
+        if flags is None:
+            flags = self.structure_flags(A, A)
+        out = dict(sm=self.empty(B, T, n), sc=self.empty(B, T, n, n) if covariances else None,
+                   proj_mean=self.empty(B, T, p), proj_var=self.empty(B, T, p),
+                   state_var=self.empty(B, T, n) if state_variances else None,
+                   status=self.empty(B, dtype=torch.int32))
+        rc = self.lib.mkf_smoother_project(B, T, n, _ptr(fm), _ptr(fc), _ptr(pm), _ptr(pc),
+                                           _ptr(A), self._stride(A, 2), int(flags), p, _ptr(Hp), self._stride(Hp, 2),
+                                           _ptr(out["sm"]), _ptr(out["sc"]), _ptr(out["proj_mean"]),
+                                           _ptr(out["proj_var"]), _ptr(out["state_var"]), _ptr(out["status"]),
+                                           self._stream())
+        _lib.check(self.lib, rc, "mkf_smoother_project")
+        return out
+
     def project(self, means, covs, Hp, variances=True):
         """H x_t and max(diag(H P_t H^T), 0) for all t (kalmanfilter.py:596-602)."""
         means, covs, Hp = self.tensor(means), self.tensor(covs), self.tensor(Hp)

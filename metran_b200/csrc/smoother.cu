@@ -37,7 +37,16 @@ struct SmootherArgs {
     double *sm, *sc;
     int32_t *status;
     int smem_model;
+    // fused epilogue (mkf_smoother_project): projections of the smoothed moments, written while the
+    // covariance of the step is still on chip
+    int p;                      // projected series (0 = none)
+    const double *Hp;           // [p][n] per model
+    int64_t Hp_stride;
+    double *pmean, *pvar;       // [B][T][p]
+    double *svar;               // [B][T][n] diag of the smoothed covariance (may be NULL)
 };
+
+__device__ __forceinline__ int64_t base_of(int64_t b, int64_t T) { return b * T; }
 
 template <int NP>
 __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const SmootherArgs a) {
@@ -63,6 +72,7 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
     double *sv = sm_;   sm_ += NP;        // broadcast vector
     double *sa = sm_;   sm_ += NP;        // diag(A)
     double *sinv = sm_; sm_ += NP;        // 1 / L_ii
+    double *sHp = sm_;  sm_ += (size_t)a.p * NP;   // projection matrix rows (fused epilogue)
     double *sA = sm_;                     // full A (only when not diagonal)
 
     const double *Ab = a.A + b * a.A_stride;
@@ -72,6 +82,34 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
             int rr = i / NP, c = i % NP;
             sA[rr * LD + c] = (rr < n && c < n) ? Ab[rr * n + c] : 0.0;
         }
+    for (int i = r; i < a.p * NP; i += NP) {
+        const int j = i / NP, c = i % NP;
+        sHp[i] = (c < n) ? a.Hp[b * a.Hp_stride + j * n + c] : 0.0;
+    }
+    // Fused projections (SPKalmanFilter.simulate, kalmanfilter.py:596-602): H x_s[t] and
+    // max(diag(H P_s[t] H^T), 0) from the row of P_s this lane holds in shared memory.
+    auto project = [&](int64_t t, double xs_r) {
+        if (a.p <= 0) return;
+        if (a.svar && r < n) a.svar[(base_of(b, a.T) + t) * n + r] = sPs[r * LD + r];
+        for (int j = 0; j < a.p; ++j) {
+            const double *h = sHp + j * NP;
+            double u = 0.0;
+#pragma unroll
+            for (int c = 0; c < NP; c += 2) {
+                const double2 pr = *reinterpret_cast<const double2 *>(sPs + r * LD + c);
+                const double2 hc = *reinterpret_cast<const double2 *>(h + c);
+                u = fma(pr.x, hc.x, u);
+                u = fma(pr.y, hc.y, u);
+            }
+            const double hr = h[r];
+            const double var = group_sum<NP>(hr * u, gmask);
+            const double mu = group_sum<NP>(hr * xs_r, gmask);
+            if (r == 0) {
+                a.pmean[(base_of(b, a.T) + t) * a.p + j] = mu;
+                a.pvar[(base_of(b, a.T) + t) * a.p + j] = fmax(var, 0.0);
+            }
+        }
+    };
 
     const int64_t T = a.T;
     const int64_t base = b * T;
@@ -87,11 +125,12 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
         for (int c = 0; c < NP; ++c) {
             const double v = (rv && c < n) ? src[(int64_t)c * n] : 0.0;
             sPs[r * LD + c] = v;
-            if (rv && c < n) dst[(int64_t)c * n] = v;
+            if (rv && c < n && a.sc) dst[(int64_t)c * n] = v;
         }
         if (rv) a.sm[(base + T - 1) * n + r] = xs;
     }
     __syncwarp(gmask);
+    project(T - 1, xs);
 
     // For NP <= 8 the inputs of step t-1 are fetched into registers while step t computes
     // (global-load latency off the critical path); at NP >= 16 the extra registers spill.
@@ -249,11 +288,12 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
             }
             const double s = s0 + s1;
             sPs[r * LD + j] = s;
-            if (rv) dst[(int64_t)j * n] = s;
+            if (rv && a.sc) dst[(int64_t)j * n] = s;
         }
         xs = xnew;
         if (rv) a.sm[(base + t) * n + r] = xs;
         __syncwarp(gmask);  // shared buffers are rewritten next step
+        project(t, xs);
     }
     if (r == 0 && a.status) a.status[b] = status;
 }
@@ -262,7 +302,7 @@ template <int NP>
 int launch_smoother(SmootherArgs a, cudaStream_t stream) {
     constexpr int LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    int per = 5 * NP * LD + 3 * NP + (diagA ? 0 : NP * LD);
+    int per = 5 * NP * LD + 3 * NP + a.p * NP + (diagA ? 0 : NP * LD);
     per = (per + 1) & ~1;
     a.smem_model = per;
     int threads = (NP == 32) ? 64 : 128;
@@ -323,17 +363,20 @@ __global__ void __launch_bounds__(128) project_kernel(int64_t B, int64_t T, int 
 
 }  // namespace
 
-extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, const double *fc,
-                            const double *pm, const double *pc, const double *A, int64_t A_stride,
-                            uint32_t flags, double *sm, double *sc, int32_t *status, void *stream) {
-    mkf_host::NvtxRange nvtx_range("mkf_smoother");
-    if (B < 0 || T < 0 || n <= 0) return MKF_ERR_BAD_ARG;
-    if (!fm || !fc || !pm || !pc || !A || !sm || !sc) return MKF_ERR_BAD_ARG;
-    if (n > 32) return MKF_ERR_UNSUPPORTED;
+static int smoother_entry(int64_t B, int64_t T, int32_t n, const double *fm, const double *fc, const double *pm,
+                          const double *pc, const double *A, int64_t A_stride, uint32_t flags, int32_t p,
+                          const double *Hp, int64_t Hp_stride, double *sm, double *sc, double *proj_mean,
+                          double *proj_var, double *state_var, int32_t *status, void *stream) {
+    if (B < 0 || T < 0 || n <= 0 || p < 0) return MKF_ERR_BAD_ARG;
+    if (!fm || !fc || !pm || !pc || !A || !sm) return MKF_ERR_BAD_ARG;
+    if (p == 0 && !sc) return MKF_ERR_BAD_ARG;
+    if (p > 0 && (!Hp || !proj_mean || !proj_var)) return MKF_ERR_BAD_ARG;
+    if (n > 32 || p > 256) return MKF_ERR_UNSUPPORTED;
     if (B == 0 || T == 0) return MKF_OK;
     SmootherArgs a{};
     a.B = B; a.T = T; a.n = n; a.fm = fm; a.fc = fc; a.pm = pm; a.pc = pc;
     a.A = A; a.A_stride = A_stride; a.flags = flags; a.sm = sm; a.sc = sc; a.status = status;
+    a.p = p; a.Hp = Hp; a.Hp_stride = Hp_stride; a.pmean = proj_mean; a.pvar = proj_var; a.svar = state_var;
     cudaStream_t s = (cudaStream_t)stream;
     if (n <= 4) return launch_smoother<4>(a, s);
     if (n <= 8) return launch_smoother<8>(a, s);
@@ -343,6 +386,25 @@ extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, c
 #endif
     if (MKF_SMOOTHER_WIDE) return launch_smoother_wide(a, s);      // four warps per model (smoother_wide.cuh)
     return launch_smoother<32>(a, s);
+}
+
+extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, const double *fc,
+                            const double *pm, const double *pc, const double *A, int64_t A_stride,
+                            uint32_t flags, double *sm, double *sc, int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_smoother");
+    return smoother_entry(B, T, n, fm, fc, pm, pc, A, A_stride, flags, 0, nullptr, 0, sm, sc, nullptr, nullptr,
+                          nullptr, status, stream);
+}
+
+extern "C" int mkf_smoother_project(int64_t B, int64_t T, int32_t n, const double *fm, const double *fc,
+                                    const double *pm, const double *pc, const double *A, int64_t A_stride,
+                                    uint32_t flags, int32_t p, const double *Hp, int64_t Hp_stride, double *sm,
+                                    double *sc, double *proj_mean, double *proj_var, double *state_var,
+                                    int32_t *status, void *stream) {
+    mkf_host::NvtxRange nvtx_range("mkf_smoother_project");
+    if (p <= 0) return MKF_ERR_BAD_ARG;
+    return smoother_entry(B, T, n, fm, fc, pm, pc, A, A_stride, flags, p, Hp, Hp_stride, sm, sc, proj_mean, proj_var,
+                          state_var, status, stream);
 }
 
 extern "C" int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p, const double *means,

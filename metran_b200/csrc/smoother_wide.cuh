@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     double *sa = sm_;    sm_ += NP;        // diag(A)
     double *sxs = sm_;   sm_ += NP;        // x_s[t]
     double *stage = sm_; sm_ += 2 * 2 * NP * NP;   // [buffer][P_p | P_f][n*n] as they lie in global memory
+    double *sHp = sm_;   sm_ += (size_t)a.p * NP;  // projection matrix rows (fused epilogue)
     double *sA = sm_;                      // full A (only when not diagonal)
 
     const double *Ab = a.A + b * a.A_stride;
@@ -56,6 +57,34 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     const int64_t base = b * T;
     const int nn = n * n;
     int status = 0;
+    for (int i = tid; i < a.p * NP; i += kSwThreads) {
+        const int j = i / NP, c = i % NP;
+        sHp[i] = (c < n) ? a.Hp[b * a.Hp_stride + j * n + c] : 0.0;
+    }
+    // fused projections of the smoothed moments (kalmanfilter.py:596-602) from sPs / sxs: warp w takes
+    // the series w, w + 4, ...; call between two block barriers
+    auto project = [&](int64_t t) {
+        if (a.p <= 0) return;
+        if (a.svar && tid < n) a.svar[(base + t) * n + tid] = sPs[tid * LD + tid];
+        for (int j = w; j < a.p; j += 4) {
+            const double *h = sHp + j * NP;
+            double u = 0.0;
+#pragma unroll
+            for (int c = 0; c < NP; c += 2) {
+                const double2 pr = *reinterpret_cast<const double2 *>(sPs + l * LD + c);
+                const double2 hc = *reinterpret_cast<const double2 *>(h + c);
+                u = fma(pr.x, hc.x, u);
+                u = fma(pr.y, hc.y, u);
+            }
+            const double hr = h[l];
+            const double var = group_sum<32>(hr * u);
+            const double mu = group_sum<32>(hr * sxs[l]);
+            if (l == 0) {
+                a.pmean[(base + t) * a.p + j] = mu;
+                a.pvar[(base + t) * a.p + j] = fmax(var, 0.0);
+            }
+        }
+    };
 
     auto issue_step = [&](int64_t t, int buf) {     // inputs of backward step t: P_p[t+1], P_f[t]
         if (t >= 0) {
@@ -76,7 +105,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         double v = 0.0;
         if (rr < n && c < n) {
             v = a.fc[(base + T - 1) * nn + rr * n + c];
-            a.sc[(base + T - 1) * nn + rr * n + c] = v;
+            if (a.sc) a.sc[(base + T - 1) * nn + rr * n + c] = v;
         }
         sPs[rr * LD + c] = v;
     }
@@ -87,6 +116,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     }
     issue_step(T - 2, 0);
     __syncthreads();
+    project(T - 1);
 
     int buf = 0;
     for (int64_t t = T - 2; t >= 0; --t, buf ^= 1) {
@@ -288,10 +318,11 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 #pragma unroll
             for (int c = 0; c < PW; ++c) {
                 sPs[l * LD + c0 + c] = out[c];
-                if (l < n && c0 + c < n) dst[c] = out[c];
+                if (a.sc && l < n && c0 + c < n) dst[c] = out[c];
             }
         }
         __syncthreads();
+        project(t);        // reads sPs / sxs, which the next step rewrites only after its own barriers
     }
     cp_async_wait<0>();
     // any thread that saw a non-positive pivot reports it (the factorisation is redundant: all do)
@@ -301,7 +332,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 int launch_smoother_wide(SmootherArgs a, cudaStream_t stream) {
     constexpr int NP = 32, LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    size_t per = 6 * NP * LD + 4 * NP + 4 * NP * NP + (diagA ? 0 : NP * LD);
+    size_t per = 6 * NP * LD + 4 * NP + 4 * NP * NP + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
     const size_t smem = (per + 2) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(smoother_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

@@ -392,10 +392,16 @@ class SPKalmanFilter:
             self.smoothed_state_covariances = sc
             return
         flags = h["flags"] & _lib.FLAG_A_DIAGONAL
-        sm, sc, status = eng.smoother(h["fm"], h["fc"], h["pm"], h["pc"], A, flags=flags)
+        # the projections every consumer of the smoother asks for (simulate(), kalmanfilter.py:596-602,
+        # with a row-scaled copy of the observation matrix: metran.py:758-829) are fused into the
+        # smoother's epilogue: H x_s and diag(H P_s H^T) leave the kernel, [T,n,n] is not read back
+        Hobs = np.ascontiguousarray(self.observation_matrix, dtype=np.float64)
+        res = eng.smoother_project(h["fm"], h["fc"], h["pm"], h["pc"], A, Hobs, flags=flags)
+        sm, sc, status = res["sm"], res["sc"], res["status"]
         if int(status[0]) & _lib.STATUS_CHOL_FAILED:
             logger.warning("Kalman smoother: a predicted covariance is not positive definite.")
         self._hist["sm"], self._hist["sc"] = sm, sc
+        self._hist["proj"] = (Hobs, res["proj_mean"], res["proj_var"])
         self._arrays.pop("sm_", None)
         self._arrays.pop("sc_", None)
         if self._lazy is None:
@@ -404,10 +410,35 @@ class SPKalmanFilter:
 
     def simulate(self, observation_matrix, method="smoother"):
         """Projected means and variances (kalmanfilter.py:569-603), one kernel for all t."""
+        Hs = np.ascontiguousarray(observation_matrix, dtype=np.float64)
+        fused = self._fused_projection(Hs) if method != "filter" else None
+        if fused is not None:
+            return fused
         means, covs = self._moments(method)
         eng = self._device_engine()
-        mu, var = eng.project(means, covs, np.ascontiguousarray(observation_matrix, dtype=np.float64))
+        mu, var = eng.project(means, covs, Hs)
         return list(mu[0].cpu().numpy()), list(var[0].cpu().numpy())
+
+    def _fused_projection(self, Hs):
+        """simulate() from the smoother's fused epilogue when Hs is the observation matrix with its
+        rows scaled (what Metran passes: H * oseries_std, metran.py:775-829): H_s x = s * (H x) and
+        diag(H_s P H_s^T) = s^2 * diag(H P H^T)."""
+        h = self._hist
+        if h is None or "proj" not in h:
+            return None
+        Hobs, pmean, pvar = h["proj"]
+        if Hs.shape != Hobs.shape:
+            return None
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = np.where(Hobs != 0.0, Hs / Hobs, np.nan)
+        if np.any((Hobs == 0.0) & (Hs != 0.0)) or np.all(np.isnan(ratio), axis=1).any():
+            return None
+        scale = np.nanmax(ratio, axis=1)
+        if not np.array_equal(Hobs * scale[:, None], Hs):
+            return None
+        mu = pmean[0].cpu().numpy() * scale[None, :]
+        var = pvar[0].cpu().numpy() * (scale * scale)[None, :]
+        return list(mu), list(var)
 
     def decompose(self, observation_matrix, method="smoother"):
         """Specific / common dynamic factor contributions (kalmanfilter.py:605-644)."""

@@ -218,6 +218,28 @@ class FakeLib:
                 st_[b] = 0
         return 0
 
+    def mkf_smoother_project(self, B, T, n, fm, fc, pm, pc, A, As, flags, p, Hp, Hs, sm, sc, pmean, pvar, svar,
+                             status, stream):
+        self.calls.append(("mkf_smoother_project", B, T, n, p))
+        fm_, fc_ = _arr(fm, (B, T, n)), _arr(fc, (B, T, n, n))
+        pm_, pc_ = _arr(pm, (B, T, n)), _arr(pc, (B, T, n, n))
+        sm_, sc_ = _arr(sm, (B, T, n)), _arr(sc, (B, T, n, n))
+        mo, vo, so = _arr(pmean, (B, T, p)), _arr(pvar, (B, T, p)), _arr(svar, (B, T, n))
+        st_ = _arr(status, (B,), np.int32)
+        for b in range(B):
+            s1, s2 = ko.kalmansmoother(fm_[b], fc_[b], pm_[b], pc_[b], _model(A, b, As, (n, n)))
+            sm_[b] = s1
+            if sc_ is not None:
+                sc_[b] = s2
+            H = _model(Hp, b, Hs, (p, n))
+            mo[b] = s1 @ H.T
+            vo[b] = np.maximum(np.einsum("ij,tjk,ik->ti", H, s2, H), 0)
+            if so is not None:
+                so[b] = np.diagonal(s2, axis1=1, axis2=2)
+            if st_ is not None:
+                st_[b] = 0
+        return 0
+
     def mkf_project(self, B, T, n, p, means, covs, Hp, Hs, mout, vout, stream):
         self.calls.append(("mkf_project", B, T, n, p))
         mu, cv = _arr(means, (B, T, n)), _arr(covs, (B, T, n, n))

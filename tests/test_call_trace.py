@@ -101,8 +101,11 @@ def test_replay_on_the_host_stand_in():
     names = [c[0] for c in eng.lib.calls]
     # every run_filter (77 objective evaluations + 3 inside run_smoother) is ONE log-likelihood call
     # on the compacted grid; the history kernel only runs where state arrays were read
-    assert names.count("mkf_dfm_loglik_compact") == 80 and names.count("mkf_smoother") == 3
+    assert names.count("mkf_dfm_loglik_compact") == 80 and names.count("mkf_smoother_project") == 3
     assert names.count("mkf_filter_history") < 20
+    # the smoother-based simulate() calls are served by the fused epilogue: mkf_project only runs for
+    # the decomposition and the method="filter" getters
+    assert names.count("mkf_project") <= 4, names.count("mkf_project")
 
 
 @pytest.mark.gpu

@@ -275,3 +275,22 @@ def test_dfm_history_batch_matches_generic_kernel(eng):
         _, _, _, fm, fc, pm, pc = ko.seqkalmanfilter(obs, A[b], Q[b], H[b], np.zeros(m), oi, oc, np.zeros(n), np.eye(n))
         np.testing.assert_allclose(_np(out["fc"])[b], fc, rtol=0, atol=1e-9)
         np.testing.assert_allclose(_np(out["pm"])[b], pm, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag", ["dfm_n8_m5_miss30", "dfm_n3_m2_miss50", "dense_n16_m7", "dense_n32_m64", "dense_n20_m33"])
+def test_smoother_with_fused_projections(eng, cases, tag):
+    """mkf_smoother_project: the projections written from the smoother's epilogue equal
+    mkf_project applied to the materialised covariances, and the smoothed covariances may be skipped."""
+    c = cases[tag]
+    out = eng.filter_history(c["y"][None], c["A"], c["Q"], c["H"], c["R"], x0=c["x0"][None], P0=c["P0"][None])
+    sm, sc, _ = eng.smoother(out["fm"], out["fc"], out["pm"], out["pc"], c["A"])
+    Hs = c["H"] * np.linspace(0.5, 2.0, c["H"].shape[0])[:, None]
+    mu, var = eng.project(sm, sc, Hs)
+    res = eng.smoother_project(out["fm"], out["fc"], out["pm"], out["pc"], c["A"], Hs)
+    assert torch.equal(res["sm"], sm) and torch.equal(res["sc"], sc)
+    np.testing.assert_allclose(_np(res["proj_mean"]), _np(mu), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(_np(res["proj_var"]), _np(var), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(_np(res["state_var"])[0], np.diagonal(c["sc"], axis1=1, axis2=2), rtol=0, atol=1e-8)
+    lean = eng.smoother_project(out["fm"], out["fc"], out["pm"], out["pc"], c["A"], Hs, covariances=False,
+                                state_variances=False)
+    assert lean["sc"] is None and torch.equal(lean["proj_var"], res["proj_var"]) and torch.equal(lean["sm"], sm)

@@ -54,7 +54,7 @@ def test_metran_solve_and_getters_through_installed_engine(installed, b21):
 
     p = pd.Series(b21["alpha_opt"], index=mt.parameters.index)
     np.testing.assert_allclose(mt.get_state_means(p=p).values[sel], b21["state_means"], atol=1e-9)
-    assert "mkf_filter_history" in [c[0] for c in eng.lib.calls] and "mkf_smoother" in [c[0] for c in eng.lib.calls]
+    assert "mkf_filter_history" in [c[0] for c in eng.lib.calls] and "mkf_smoother_project" in [c[0] for c in eng.lib.calls]
     np.testing.assert_allclose(mt.get_state_variances(p=p).values[sel], b21["state_variances"], atol=1e-9)
     np.testing.assert_allclose(mt.get_simulated_means(p=p).values[sel], b21["sim_means"], atol=1e-9)
     np.testing.assert_allclose(mt.get_simulated_variances(p=p).values[sel], b21["sim_variances"], atol=1e-9)
