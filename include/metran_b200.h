@@ -59,7 +59,8 @@ extern "C" {
 
 /* per-model status bits (int32) */
 #define MKF_STATUS_NONPOSITIVE_F 1 /* an innovation variance f <= 0 or non-finite */
-#define MKF_STATUS_CHOL_FAILED 2   /* smoother: predicted covariance not positive definite */
+#define MKF_STATUS_CHOL_FAILED 2   /* smoother: a predicted covariance was not positive definite; the
+                                      singular directions got zero gain (the reference's pinv does the same) */
 
 /* flags */
 #define MKF_FLAG_A_DIAGONAL 1 /* caller guarantees A is diagonal (Metran: always)  */

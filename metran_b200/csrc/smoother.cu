@@ -178,13 +178,26 @@ __global__ void __launch_bounds__(NP == 32 ? 64 : 128) smoother_kernel(const Smo
             *reinterpret_cast<double2 *>(sD + r * LD + c) = make_double2(ps.x - p0, ps.y - p1);
         }
         const double delta = xs - xp;
+        double d0 = 0.0;                         // original diagonal entry of this lane's row
+#pragma unroll
+        for (int c = 0; c < NP; ++c) d0 = (c == r) ? L[c] : d0;
+        double dmax = rv ? d0 : 0.0;             // largest diagonal entry: scale of pinv's cut-off
+#pragma unroll
+        for (int off = NP / 2; off > 0; off >>= 1) dmax = fmax(dmax, __shfl_xor_sync(gmask, dmax, off, NP));
 
         // ---- Cholesky P_p = L L^T (padded rows/cols are the identity) ---------------------
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             const double pjj = __shfl_sync(gmask, L[j], j, NP);
-            if (!(pjj > 0.0)) status |= MKF_STATUS_CHOL_FAILED;
-            const double inv = rsqrt(pjj);
+            // A pivot that is not positive relative to its original diagonal entry belongs to a direction in
+            // which P_p is (numerically) singular -- a state without process noise that the data determine
+            // exactly (communality 1 with R = 0).  The reference's pinv (kalmanfilter.py:455) assigns such a
+            // direction zero gain (singular values below 1e-15 of the largest); zeroing the column of L and
+            // its reciprocal does the same here, and the model is flagged instead of returning NaN.
+            const double d0j = __shfl_sync(gmask, d0, j, NP);
+            const bool okp = pjj > 1.5e-14 * d0j && pjj > 1e-15 * dmax && pjj > 0.0;
+            if (!okp) status |= MKF_STATUS_CHOL_FAILED;
+            const double inv = okp ? rsqrt(pjj) : 0.0;
             const double ljj = pjj * inv;
             const double lrj = (r == j) ? ljj : ((r > j) ? L[j] * inv : 0.0);
             L[j] = lrj;

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     double *sinv = sm_;  sm_ += NP;        // 1 / L_ii
     double *sa = sm_;    sm_ += NP;        // diag(A)
     double *sxs = sm_;   sm_ += NP;        // x_s[t]
+    double *sdg = sm_;   sm_ += NP;        // original diagonal of P_p[t+1] (singularity test of the pivots)
     double *stage = sm_; sm_ += 2 * 2 * NP * NP;   // [buffer][P_p | P_f][n*n] as they lie in global memory
     double *sHp = sm_;   sm_ += (size_t)a.p * NP;  // projection matrix rows (fused epilogue)
     double *sA = sm_;                      // full A (only when not diagonal)
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
                 const double pp = in ? sp[l * n + cc] : ((l == cc) ? 1.0 : 0.0);   // padding: identity
                 const double pf = in ? sf[l * n + cc] : 0.0;
                 sL[l * LD + cc] = pp;
+                if (l == cc) sdg[l] = pp;
                 sPf[l * LD + cc] = pf;
                 sD[l * LD + cc] = in ? sPs[l * LD + cc] - pp : 0.0;
             }
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         __syncthreads();
 
         // ---- 1. blocked Cholesky P_p = L L^T in sL (lower triangle) -----------------------------
+        double dmax = 0.0;                        // largest diagonal entry: scale of pinv's cut-off
+        for (int i = 0; i < n; ++i) dmax = fmax(dmax, sdg[i]);
 #pragma unroll 1
         for (int p = 0; p < NP / PW; ++p) {
             const int j0 = p * PW;
@@ -158,8 +162,10 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 #pragma unroll
             for (int j = 0; j < PW; ++j) {
                 const double pjj = Ld[lt(j, j)];
-                if (!(pjj > 0.0)) status |= MKF_STATUS_CHOL_FAILED;
-                const double iv = rsqrt(pjj);
+                // numerically singular direction: zero gain, as the reference's pinv (see smoother.cu)
+                const bool okp = pjj > 1.5e-14 * sdg[j0 + j] && pjj > 1e-15 * dmax && pjj > 0.0;
+                if (!okp) status |= MKF_STATUS_CHOL_FAILED;
+                const double iv = okp ? rsqrt(pjj) : 0.0;
                 inv[j] = iv;
                 Ld[lt(j, j)] = pjj * iv;
 #pragma unroll
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 int launch_smoother_wide(SmootherArgs a, cudaStream_t stream) {
     constexpr int NP = 32, LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    size_t per = 6 * NP * LD + 4 * NP + 4 * NP * NP + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
+    size_t per = 6 * NP * LD + 5 * NP + 4 * NP * NP + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
     const size_t smem = (per + 2) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(smoother_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

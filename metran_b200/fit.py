@@ -15,11 +15,14 @@ projected step; its iterates differ from scipy's, its optimum does not.
 """
 import numpy as np
 
-__all__ = ["fit_dfm_batch", "BatchFitResult"]
+__all__ = ["fit_dfm_batch", "BatchFitResult", "REASONS"]
+
+REASONS = ("gtol", "ftol", "maxiter", "linesearch_failed", "nonfinite_start")
 
 
 class BatchFitResult(dict):
-    """alpha[B,n], obj[B] (-2 log L at the optimum), nit, nfev (per model), converged[B]."""
+    """alpha[B,n], obj[B] (-2 log L at the optimum), nit, nfev (per model), converged[B] (the gradient
+    or function-decrease criterion was met after a successful step) and reason[B]: one of REASONS."""
 
     __getattr__ = dict.__getitem__
 
@@ -66,6 +69,7 @@ def fit_dfm_batch(engine, y, factors, alpha0=10.0, dt=1.0, warmup=1, maxiter=60,
     Hinv = np.broadcast_to(np.eye(n), (B, n, n)).copy()
     active = np.isfinite(f)
     nit = np.zeros(B, dtype=np.int64)
+    reason = np.where(active, REASONS.index("maxiter"), REASONS.index("nonfinite_start"))
     for _ in range(maxiter):
         if not active.any():
             break
@@ -108,7 +112,13 @@ def fit_dfm_batch(engine, y, factors, alpha0=10.0, dt=1.0, warmup=1, maxiter=60,
         df = f - f_new
         nit += moved
         theta, f, g = theta_new, f_new, g_new
-        done = (~moved) | (np.abs(g).max(axis=1) < gtol) | (df <= ftol * np.maximum(1.0, np.abs(f)))
-        active &= ~done
+        hit_g = moved & (np.abs(g).max(axis=1) < gtol)
+        hit_f = moved & ~hit_g & (df <= ftol * np.maximum(1.0, np.abs(f)))
+        failed = active & ~moved
+        reason = np.where(active & hit_g, REASONS.index("gtol"), reason)
+        reason = np.where(active & hit_f, REASONS.index("ftol"), reason)
+        reason = np.where(failed, REASONS.index("linesearch_failed"), reason)
+        active &= ~(hit_g | hit_f | failed)
     return BatchFitResult(alpha=np.exp(theta), obj=f, nit=nit, nfev=nfev, launches=nfev,
-                          converged=~active, grad=g)
+                          converged=(reason == REASONS.index("gtol")) | (reason == REASONS.index("ftol")),
+                          reason=np.array(REASONS)[reason], grad=g)

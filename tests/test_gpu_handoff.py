@@ -125,3 +125,22 @@ def test_handoff_actually_taken(eng):
     t_off, m_off = timed(0)
     assert torch.equal(m_on, m_off)
     assert t_on < t_off, "hand-off path (%.3f ms) not faster than the single kernel (%.3f ms)" % (t_on, t_off)
+
+
+def test_batch_permutation_dense_bit_identical_and_gaps_within_1e_10(eng):
+    """for fully observed data a model's value depends on its own inputs only
+    (any permutation / split of the batch gives the same bits); with gaps the warp-level switch points
+    move results at the 1e-13 relative level."""
+    y, alpha, G = _dense_batch(5, 3, 96, 1300, seed=11)
+    perm = np.random.default_rng(0).permutation(96)
+    a = eng.dfm_loglik_alpha(y, alpha, G)[0]
+    b = eng.dfm_loglik_alpha(y[perm].copy(), alpha[perm].copy(), G[perm].copy())[0]
+    assert torch.equal(a[torch.as_tensor(perm, device=a.device)], b)
+    c = eng.dfm_loglik_alpha(y[:40].copy(), alpha[:40].copy(), G[:40].copy())[0]
+    assert torch.equal(a[:40], c)
+    yg = y.copy()
+    yg[7, 900:903] = np.nan
+    yg[50, 1100, 2] = np.nan
+    ag = eng.dfm_loglik_alpha(yg, alpha, G)[0]
+    bg = eng.dfm_loglik_alpha(yg[perm].copy(), alpha[perm].copy(), G[perm].copy())[0]
+    assert float((ag[torch.as_tensor(perm, device=a.device)] - bg).abs().max()) <= 1e-10

@@ -294,3 +294,34 @@ def test_smoother_with_fused_projections(eng, cases, tag):
     lean = eng.smoother_project(out["fm"], out["fc"], out["pm"], out["pc"], c["A"], Hs, covariances=False,
                                 state_variances=False)
     assert lean["sc"] is None and torch.equal(lean["proj_var"], res["proj_var"]) and torch.equal(lean["sm"], sm)
+
+
+@pytest.mark.parametrize("n_extra", [0, 14])
+def test_smoother_with_a_singular_predicted_covariance(eng, n_extra):
+    """A series with communality 1 and R = 0 has no specific process noise: its state is known
+    exactly after the first observation and P_p is singular in that direction.  The reference's pinv
+    (kalmanfilter.py:455) gives it zero gain; the Cholesky-based smoother must do the same (finite
+    results, status flagged) instead of NaN.  n_extra pads the state to exercise the wide kernel."""
+    rng = np.random.default_rng(3)
+    m, k, T = 4, 2, 150
+    G = rng.uniform(0.3, 0.6, (m, k))
+    G[1] /= np.linalg.norm(G[1])                    # communality exactly 1 -> q = 0 for series 1
+    n = m + k + n_extra
+    alpha = rng.uniform(5, 40, n)
+    phi = np.exp(-1.0 / alpha)
+    comm = np.concatenate([(G ** 2).sum(1), np.zeros(k + n_extra)])
+    q = (1 - phi ** 2) * np.where(np.arange(n) < m, 1 - comm[:n], 1.0)
+    q[1] = 0.0
+    H = np.zeros((m, n)); H[:, :m] = np.eye(m); H[:, m:m + k] = G
+    A, Q, R = np.diag(phi), np.diag(q), np.zeros(m)
+    y = rng.standard_normal((T, m))
+    y[rng.random(y.shape) < 0.2] = np.nan
+    out = eng.filter_history(y[None], A, Q, H, R)
+    sm, sc, st = eng.smoother(out["fm"], out["fc"], out["pm"], out["pc"], A)
+    assert torch.isfinite(sm).all() and torch.isfinite(sc).all()
+    assert int(st[0]) & 2                             # MKF_STATUS_CHOL_FAILED: flagged, not fatal
+    obs, idx, cnt = ko.pack_observations(y)
+    _, _, _, fm, fc, pm, pc = ko.seqkalmanfilter(obs, A, Q, H, R, idx, cnt, np.zeros(n), np.eye(n))
+    s1, s2 = ko.kalmansmoother(fm, fc, pm, pc, A)   # pinv-based restatement of the reference
+    np.testing.assert_allclose(_np(sm)[0], s1, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(_np(sc)[0], s2, rtol=0, atol=1e-8)

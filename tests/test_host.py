@@ -290,7 +290,13 @@ def test_batched_fit_reaches_the_reference_optimum(eng, nbmodel):
     starts = np.array([[10.0, 10.0, 10.0], [4.0, 30.0, 15.0], [25.0, 6.0, 40.0]])
     res = fit_dfm_batch(eng, np.broadcast_to(y, (B,) + y.shape).copy(),
                         np.broadcast_to(g["factors"], (B,) + g["factors"].shape).copy(), alpha0=starts)
-    assert res.converged.all()
+    assert res.converged.all() and set(res.reason) <= {"gtol", "ftol"}
+    # a model whose objective is not finite at the start is reported as such, not as converged
+    ybad = np.broadcast_to(y, (B,) + y.shape).copy()
+    fbad = np.broadcast_to(g["factors"], (B,) + g["factors"].shape).copy()
+    fbad[1] = np.nan
+    res_bad = fit_dfm_batch(eng, ybad, fbad, alpha0=starts, maxiter=3)
+    assert not res_bad.converged[1] and res_bad.reason[1] == "nonfinite_start"
     # reference optimum on the same truncated data through the single-model path
     from metran_b200.dfm import DynamicFactorModel
 
