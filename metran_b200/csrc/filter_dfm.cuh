@@ -150,6 +150,9 @@ __host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false,
 #ifndef MKF_FREEZE
 #define MKF_FREEZE 1
 #endif
+#ifndef MKF_CAPTURE_SPLIT
+#define MKF_CAPTURE_SPLIT 0       // 1: the capture step is a separate copy of the factor-only step
+#endif
 #ifndef MKF_FREEZE_NCONV
 #define MKF_FREEZE_NCONV 2        // consecutive unchanged checks before a lane holds its covariance
 #endif
@@ -761,6 +764,20 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                         double qc[K];
 #pragma unroll
                         for (int j = 0; j < K; ++j) qc[j] = MKF_QQ(M + j);
+#if MKF_CAPTURE_SPLIT
+                        // the one step that stores its reciprocal pivots, multipliers and gains over S0 / QG
+                        // (capture_next is warp-uniform) is a separate copy of the code: the 30 stores and
+                        // their predicates stay out of the loop every other step runs
+                        if (kFreeze && capture_next) {
+                            collapsed_step_impl<M, K, true>(
+                                x, P, phi, qc, yq, yc, [&](int i) { return lds_f64(ccs + i * 32); },
+                                [&](int i, double v) { sts_f64(ccs + (M * K + i) * 32, v); }, sigma, stepprod, bad);
+                        } else {
+                            collapsed_step_impl<M, K, false>(
+                                x, P, phi, qc, yq, yc, [&](int i) { return lds_f64(ccs + i * 32); },
+                                [](int, double) {}, sigma, stepprod, bad);
+                        }
+#else
                         // one code path: when capture_next is set (warp-uniform) the step also stores
                         // its reciprocal pivots, multipliers and gains over S0 / QG (predicated stores)
                         collapsed_step_impl<M, K, kFreeze>(
@@ -769,6 +786,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                                 if (capture_next) sts_f64(ccs + (M * K + i) * 32, v);
                             },
                             sigma, stepprod, bad);
+#endif
                         if (kFreeze) {
                             if (lane_holds) {
 #pragma unroll

@@ -298,10 +298,10 @@ def test_smoother_with_fused_projections(eng, cases, tag):
 
 @pytest.mark.parametrize("n_extra", [0, 14])
 def test_smoother_with_a_singular_predicted_covariance(eng, n_extra):
-    """A series with communality 1 and R = 0 has no specific process noise: its state is known
-    exactly after the first observation and P_p is singular in that direction.  The reference's pinv
-    (kalmanfilter.py:455) gives it zero gain; the Cholesky-based smoother must do the same (finite
-    results, status flagged) instead of NaN.  n_extra pads the state to exercise the wide kernel."""
+    """A state without process noise (communality 1: q = 0) that starts exactly known (P0_ii = 0) keeps a
+    zero row and column in every covariance: P_p is singular.  The reference's pinv (kalmanfilter.py:455)
+    gives that direction zero gain; the Cholesky-based smoother must do the same (finite results equal to
+    the pinv ones, status flagged) instead of NaN.  n_extra pads the state to exercise the wide kernel."""
     rng = np.random.default_rng(3)
     m, k, T = 4, 2, 150
     G = rng.uniform(0.3, 0.6, (m, k))
@@ -316,12 +316,15 @@ def test_smoother_with_a_singular_predicted_covariance(eng, n_extra):
     A, Q, R = np.diag(phi), np.diag(q), np.zeros(m)
     y = rng.standard_normal((T, m))
     y[rng.random(y.shape) < 0.2] = np.nan
-    out = eng.filter_history(y[None], A, Q, H, R)
+    P0 = np.eye(n)
+    P0[1, 1] = 0.0
+    out = eng.filter_history(y[None], A, Q, H, R, x0=np.zeros((1, n)), P0=P0[None])
     sm, sc, st = eng.smoother(out["fm"], out["fc"], out["pm"], out["pc"], A)
     assert torch.isfinite(sm).all() and torch.isfinite(sc).all()
     assert int(st[0]) & 2                             # MKF_STATUS_CHOL_FAILED: flagged, not fatal
     obs, idx, cnt = ko.pack_observations(y)
-    _, _, _, fm, fc, pm, pc = ko.seqkalmanfilter(obs, A, Q, H, R, idx, cnt, np.zeros(n), np.eye(n))
+    _, _, _, fm, fc, pm, pc = ko.seqkalmanfilter(obs, A, Q, H, R, idx, cnt, np.zeros(n), P0)
+    assert min(np.linalg.eigvalsh(pc[t]).min() for t in range(T)) < 1e-15          # really singular
     s1, s2 = ko.kalmansmoother(fm, fc, pm, pc, A)   # pinv-based restatement of the reference
     np.testing.assert_allclose(_np(sm)[0], s1, rtol=0, atol=1e-8)
     np.testing.assert_allclose(_np(sc)[0], s2, rtol=0, atol=1e-8)

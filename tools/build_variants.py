@@ -4,12 +4,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    # steady-state kernel (dfm_steady.cuh): tile length x ring depth (default 2 x 8)
-    "st_6x2": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=2"],
-    "st_6x3": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=3"],
-    # transient kernel candidates
-    "tr_rcp3": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=2", "-DMKF_RCP3=1"],
-    "tr_check1": ["-DMKF_ST_TT=6", "-DMKF_ST_STAGES=2", "-DMKF_FREEZE_EVERY_STEP=1", "-DMKF_FREEZE_NCONV=12"],
+    # transient kernel candidates (the steady kernel is the default 6 x 3)
+    "tr_capsplit": ["-DMKF_CAPTURE_SPLIT=1"],
+    "tr_capsplit_rcp3": ["-DMKF_CAPTURE_SPLIT=1", "-DMKF_RCP3=1"],
+    "tr_nconv1": ["-DMKF_FREEZE_NCONV=1"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}

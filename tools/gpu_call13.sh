@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_handoff.py -m gpu -x -q 2>&1 | tail -5
+timeout 600 python tools/probe_variants.py 2>&1 | tail -8
