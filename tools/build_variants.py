@@ -4,10 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    # transient kernel candidates (the steady kernel is the default 6 x 3)
-    "tr_capsplit": ["-DMKF_CAPTURE_SPLIT=1"],
-    "tr_capsplit_rcp3": ["-DMKF_CAPTURE_SPLIT=1", "-DMKF_RCP3=1"],
-    "tr_nconv1": ["-DMKF_FREEZE_NCONV=1"],
+    # transient kernel: plain pivot order vs the default (next pivot's reciprocal started early)
+    "tr_plain": ["-DMKF_PIVOT_AHEAD=0"],
+    "tr_ahead_rcp3": ["-DMKF_RCP3=1"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}
