@@ -27,10 +27,6 @@
 
 #include "mkf_common.cuh"
 
-#ifndef MKF_PIVOT_AHEAD
-#define MKF_PIVOT_AHEAD 1   // factor-only step: start the next pivot's reciprocal before finishing the current one
-#endif
-
 namespace mkf_dfm {
 
 // index of (r, c), r <= c, in the packed upper triangle of an N x N matrix
@@ -114,90 +110,6 @@ __host__ __device__ __forceinline__ void collapsed_step_impl(double *x, double *
         for (int j = 0; j < K; ++j) s = fma(D[i * K + j], x[M + j], s);
         v[i] = s;
     }
-#if MKF_PIVOT_AHEAD
-    // Same operations as the plain order below, arranged so that the reciprocal of the NEXT pivot is
-    // started as early as its operand exists: pivot i+1 only needs S(i+1,i+1) after elimination step
-    // i, so that one entry is updated first, its reciprocal issued, and the rest of step i (the other
-    // entries of S, T, v, the gains and the update of c, C) fills the latency of the reciprocal chain.
-    // Values and their rounding are identical to the plain order (the same FMAs on the same operands).
-    double W[M * K], S[MT], Tm[K * M];
-    auto wrow = [&](int i) {
-#pragma unroll
-        for (int l = 0; l < K; ++l) {
-            double s = D[i * K] * P[sym<N>(M, M + l)];
-#pragma unroll
-            for (int j = 1; j < K; ++j) s = fma(D[i * K + j], P[sym<N>(M + j, M + l)], s);
-            W[i * K + l] = s;
-        }
-    };
-    auto sent = [&](int i, int l) {
-        double s = ld(M * K + tri<M>(i, l));
-#pragma unroll
-        for (int j = 0; j < K; ++j) s = fma(W[i * K + j], D[l * K + j], s);
-        S[tri<M>(i, l)] = s;
-    };
-    wrow(0);
-    sent(0, 0);
-    double f = S[tri<M>(0, 0)];
-    double rf = cs_rcp(f);
-#pragma unroll
-    for (int i = 1; i < M; ++i) wrow(i);
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-#pragma unroll
-        for (int i = 0; i < M; ++i) Tm[j * M + i] = fma(-phi[M + j], W[i * K + j], ld(M * K + MT + j * M + i));
-#pragma unroll
-    for (int i = 0; i < M; ++i)
-#pragma unroll
-        for (int l = i; l < M; ++l)
-            if (!(i == 0 && l == 0)) sent(i, l);
-    // predict the factor block
-#pragma unroll
-    for (int j = 0; j < K; ++j) x[M + j] *= phi[M + j];
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-#pragma unroll
-        for (int l = j; l < K; ++l) {
-            const double t = (phi[M + j] * P[tri<N>(M + j, M + l)]) * phi[M + l];
-            P[tri<N>(M + j, M + l)] = (j == l) ? t + qc[j] : t;
-        }
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-        bad = bad || cs_bad(f);
-        double mnext = 0.0, fnext = 0.0, rfnext = 0.0;
-        if (i + 1 < M) {
-            mnext = S[tri<M>(i, i + 1)] * rf;
-            S[tri<M>(i + 1, i + 1)] = fma(-mnext, S[tri<M>(i, i + 1)], S[tri<M>(i + 1, i + 1)]);
-            fnext = S[tri<M>(i + 1, i + 1)];
-            rfnext = cs_rcp(fnext);
-        }
-        stepprod *= f;
-        sigma = fma(v[i] * v[i], rf, sigma);
-        if (CAP) cap(i, rf);
-#pragma unroll
-        for (int l = i + 1; l < M; ++l) {
-            const double mlt = (l == i + 1) ? mnext : S[tri<M>(i, l)] * rf;
-            if (CAP) cap(M + frozen_pair<M>(i, l), mlt);
-            v[l] = fma(-mlt, v[i], v[l]);
-#pragma unroll
-            for (int l2 = l; l2 < M; ++l2)
-                if (!(l == i + 1 && l2 == i + 1)) S[tri<M>(l, l2)] = fma(-mlt, S[tri<M>(i, l2)], S[tri<M>(l, l2)]);
-#pragma unroll
-            for (int j = 0; j < K; ++j) Tm[j * M + l] = fma(-mlt, Tm[j * M + i], Tm[j * M + l]);
-        }
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const double g = Tm[j * M + i] * rf;
-            if (CAP) cap(MT + j * M + i, g);
-            x[M + j] = fma(g, v[i], x[M + j]);
-#pragma unroll
-            for (int l = j; l < K; ++l) P[tri<N>(M + j, M + l)] = fma(-g, Tm[l * M + i], P[tri<N>(M + j, M + l)]);
-        }
-        f = fnext;
-        rf = rfnext;
-    }
-}
-#else
     // W = D C
     double W[M * K];
 #pragma unroll
@@ -265,7 +177,6 @@ __host__ __device__ __forceinline__ void collapsed_step_impl(double *x, double *
         }
     }
 }
-#endif
 
 template <int M, int K, class Load>
 __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, const double *phi, const double *qc,
