@@ -226,6 +226,13 @@ int mkf_project(int64_t B, int64_t T, int32_t n, int32_t p,
 int mkf_dfm_set_handoff(int enabled);
 void mkf_release_workspaces(void);
 /*
+ * mkf_dfm_filter_history writes the state arrays of n = 4 and n = 8 models with TMA tensor stores
+ * (one cp.async.bulk.tensor per array and step for a warp's 32 models) when the arrays are 16-byte
+ * aligned; mkf_dfm_set_hist_tma(0) forces the shared-memory transposition used for every other shape
+ * (same values; used by the parity tests).  Returns the previous setting.  No reference counterpart.
+ */
+int mkf_dfm_set_hist_tma(int enabled);
+/*
  * Measurement aid for the three-launch path (no reference counterpart).  With
  * mkf_dfm_set_profile(1) the library records CUDA events around each launch; afterwards
  * mkf_dfm_last_profile(stream, ms, stats) waits for `stream` and returns for the most recent

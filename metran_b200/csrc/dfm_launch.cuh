@@ -26,6 +26,36 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
     }
     const int64_t blocks = (a.B + kBlock - 1) / kBlock;
     a.ho_mode = HO_MODE_OFF;
+    // history stores: tensor maps of the four state arrays (all requested arrays or none), whole-sector
+    // stores of the step scalars when their bases allow it
+    HistMaps<HIST> hmaps;
+    a.hist_tma = 0;
+    a.hist_vec = 0;
+    if constexpr (HIST) {
+        memset(&hmaps, 0, sizeof(hmaps));
+        constexpr int N = M + K;
+        auto al32 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+        a.hist_vec = al32(a.sigma) && al32(a.detf) && al32(a.cnt);
+        if (hist_tma_shape(M, K) && hist_tma_enabled()) {
+            int mask = 0;
+            bool ok = true;
+            if (a.pc) { ok = ok && make_hist_map(&hmaps.pc, a.pc, 16, a.B, a.T, N * N / 16, MKF_HIST_TSC) == MKF_OK; mask |= HIST_TMA_PC; }
+            if (a.pm) { ok = ok && make_hist_map(&hmaps.pm, a.pm, N, a.B, a.T, 1, MKF_HIST_TSM) == MKF_OK; mask |= HIST_TMA_PM; }
+            if (a.fc) { ok = ok && make_hist_map(&hmaps.fc, a.fc, 16, a.B, a.T, N * N / 16, MKF_HIST_TSC) == MKF_OK; mask |= HIST_TMA_FC; }
+            if (a.fm) { ok = ok && make_hist_map(&hmaps.fm, a.fm, N, a.B, a.T, 1, MKF_HIST_TSM) == MKF_OK; mask |= HIST_TMA_FM; }
+            a.hist_tma = ok ? mask : 0;
+        }
+        // the step scalars as {16 steps, 32 models} boxes: all requested ones or none (a mix would put
+        // tensor stores and per-lane stores into the same staging area)
+        if (hist_tma_enabled() && (a.sigma || a.detf || a.cnt)) {
+            int mask = 0;
+            bool ok = true;
+            if (a.sigma) { ok = ok && make_scalar_map(&hmaps.sigma, a.sigma, 8, a.B, a.T) == MKF_OK; mask |= HIST_TMA_SIGMA; }
+            if (a.detf) { ok = ok && make_scalar_map(&hmaps.detf, a.detf, 8, a.B, a.T) == MKF_OK; mask |= HIST_TMA_DETF; }
+            if (a.cnt) { ok = ok && make_scalar_map(&hmaps.cnt, a.cnt, 4, a.B, a.T) == MKF_OK; mask |= HIST_TMA_CNT; }
+            if (ok) a.hist_tma |= mask;
+        }
+    }
 
     // Hand-off path: R = 0, no history, a collapse-capable shape, TMA staging and a series long
     // enough for the transient to end well before T.
@@ -62,19 +92,19 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
                 const bool prof = profile_enabled() && profile_events(hs);
                 a.ho_mode = HO_MODE_HANDOFF;   // every warp writes its ho_state: no memset needed
                 if (prof) cudaEventRecord(hs->ev[0], stream);
-                kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+                kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map, hmaps);
                 if (prof) cudaEventRecord(hs->ev[1], stream);
                 skern<<<(unsigned)blocks, 32, ssmem, stream>>>(a, smap);
                 if (prof) cudaEventRecord(hs->ev[2], stream);
                 a.ho_mode = HO_MODE_RESUME;
-                kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+                kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map, hmaps);
                 if (prof) cudaEventRecord(hs->ev[3], stream);
                 hs->profiled = prof;
                 return mkf_host::check_launch();
             }
         }
     }
-    kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map);
+    kern<<<(unsigned)blocks, kBlock, smem, stream>>>(a, map, hmaps);
     return mkf_host::check_launch();
 }
 

@@ -17,7 +17,9 @@ std::mutex g_ws_mutex;
 std::map<std::pair<int, cudaStream_t>, HandoffScratch> g_ws;
 std::atomic<int> g_handoff{1};
 std::atomic<int> g_profile{0};
+std::atomic<int> g_hist_tma{1};
 }  // namespace
+bool hist_tma_enabled() { return g_hist_tma.load() != 0; }
 
 HandoffScratch *handoff_scratch(cudaStream_t stream, size_t bytes) {
     int dev = 0;
@@ -99,6 +101,47 @@ int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t r
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                     l2_promotion_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+    return r == CUDA_SUCCESS ? MKF_OK : MKF_ERR_UNSUPPORTED;
+}
+
+int make_hist_map(CUtensorMap *map, double *p, int inner, int64_t B, int64_t T, int lines, int steps) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !p) return MKF_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) return MKF_ERR_UNSUPPORTED;
+    if (B <= 0 || T <= 0 || B >= (1LL << 31) || T * lines >= (1LL << 31)) return MKF_ERR_UNSUPPORTED;
+    const int64_t row_bytes = T * lines * inner * 8;   // one model's block
+    if (row_bytes % 16 != 0 || row_bytes >= (1LL << 40)) return MKF_ERR_UNSUPPORTED;
+    const CUtensorMapSwizzle sw = inner * 8 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : inner * 8 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : inner * 8 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                    : CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return MKF_ERR_UNSUPPORTED;
+    // dims from the innermost: {inner doubles of one 'line', models, lines over time}; the model
+    // stride is larger than the line stride on purpose: the box in shared memory is then
+    // [line][model][inner], i.e. consecutive lanes (= models) are `inner * 8` bytes apart
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)B, (cuuint64_t)(T * lines)};
+    cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)inner * 8};
+    cuuint32_t box[3] = {(cuuint32_t)inner, 32, (cuuint32_t)(lines * steps)};
+    if (lines * steps > 256) return MKF_ERR_UNSUPPORTED;
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MKF_OK : MKF_ERR_UNSUPPORTED;
+}
+
+int make_scalar_map(CUtensorMap *map, void *p, int elem_bytes, int64_t B, int64_t T) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !p || (elem_bytes != 8 && elem_bytes != 4)) return MKF_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (T * elem_bytes) % 16 != 0) return MKF_ERR_UNSUPPORTED;
+    if (B <= 0 || T <= 0 || B >= (1LL << 31) || T >= (1LL << 31)) return MKF_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)T * elem_bytes};
+    cuuint32_t box[2] = {16, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_INT32, 2, p, dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    elem_bytes == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? MKF_OK : MKF_ERR_UNSUPPORTED;
 }
 
@@ -194,6 +237,8 @@ extern "C" int mkf_dfm_filter_history(int64_t B, int64_t T, int32_t m, int32_t k
 extern "C" int mkf_dfm_set_handoff(int enabled) {
     return mkf_dfm::g_handoff.exchange(enabled ? 1 : 0);
 }
+
+extern "C" int mkf_dfm_set_hist_tma(int enabled) { return mkf_dfm::g_hist_tma.exchange(enabled ? 1 : 0); }
 
 extern "C" int mkf_dfm_set_profile(int enabled) { return mkf_dfm::g_profile.exchange(enabled ? 1 : 0); }
 

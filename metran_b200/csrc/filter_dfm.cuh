@@ -70,7 +70,23 @@ struct DfmArgs {
     int64_t ho_pitch;     // models rounded up to a multiple of 32
     int64_t *ho_tnext;    // per warp: next time step to do
     int32_t *ho_state;    // per warp: HO_*
+    // history stores (HIST builds): bit mask of the arrays written by TMA tensor stores
+    // (HIST_TMA_*; 0 = the shared-memory transposition with 256-byte STG pieces), and whether the
+    // per-step scalars can be written as whole 32-byte sectors (bases 32-byte aligned)
+    int hist_tma;
+    int hist_vec;
 };
+
+enum { HIST_TMA_PC = 1, HIST_TMA_PM = 2, HIST_TMA_FC = 4, HIST_TMA_FM = 8, HIST_TMA_STATE = 15,
+       HIST_TMA_SIGMA = 16, HIST_TMA_DETF = 32, HIST_TMA_CNT = 64, HIST_TMA_SCALARS = 112 };
+// Tensor maps of the history arrays (kernel parameter of the HIST builds only).
+template <bool HIST>
+struct HistMaps {
+    CUtensorMap pc, pm, fc, fm;      // [B][T][n][n] / [B][T][n]
+    CUtensorMap sigma, detf, cnt;    // [B][T]
+};
+template <>
+struct HistMaps<false> {};
 
 enum { HO_MODE_OFF = 0, HO_MODE_HANDOFF = 1, HO_MODE_RESUME = 2 };
 enum { HO_DONE = 0, HO_STEADY = 1, HO_RESUME = 2 };
@@ -140,7 +156,33 @@ __host__ __device__ constexpr int warp_doubles(int M, int K, bool hist = false, 
     return kStages * 32 * tile_steps(M, hist) * M + 32 * const_count(M, K) +
            ((collapse && collapse_shape(M, K)) ? 32 * collapsed_const_count(M, K) : 0);
 }
-__host__ __device__ constexpr int hist_doubles(int M, int K) { return ((M + K) + (M + K) * (M + K)) * 33; }
+// History staging.  Legacy: one record set [N + N*N][33] transposed through shared memory.  Shapes
+// with N*N a multiple of 16 doubles and N*8 a swizzle span (N = 4, 8) stage each lane's own record in
+// a swizzled box that ONE cp.async.bulk.tensor.3d per array writes out (MKF_HIST_NBUF boxes, 1 KB
+// aligned).  Both are followed by the staging of the step scalars: three boxes of 16 steps x 32
+// models for tensor stores (sigma, detf: 4 KB each, cnt: 2 KB; 1 KB aligned), or -- in the same
+// place, when the rows do not allow tensor stores -- the per-lane sector staging sigma[4][32],
+// detf[4][32] (doubles), cnt[8][32] (int32).
+#ifndef MKF_HIST_NBUF
+#define MKF_HIST_NBUF 2    // staging boxes per warp: 2 = predicted and filtered records in separate boxes
+#endif
+// Time steps staged per tensor store.  The memory system, not the SM, bounds the history kernel, and
+// it cares about the size of the contiguous pieces (tools/ubench_tma_store.cu, pure stores of this
+// pattern): 64-byte mean pieces next to 512-byte covariance pieces 4.9 TB/s, without the means 5.9,
+// 128-byte + 1-KB pieces 5.9, 1 KB alone 6.3 TB/s.
+#ifndef MKF_HIST_TSC
+#define MKF_HIST_TSC 1     // covariances: steps per store (N*N*8 bytes each)
+#endif
+#ifndef MKF_HIST_TSM
+#define MKF_HIST_TSM 4     // means: steps per store (N*8 bytes each)
+#endif
+__host__ __device__ constexpr bool hist_tma_shape(int M, int K) { return (M + K) == 4 || (M + K) == 8; }
+__host__ __device__ constexpr int hist_scalar_doubles() { return 1280 + 128; }
+__host__ __device__ constexpr int hist_doubles(int M, int K) {
+    const int n = M + K, legacy = (n + n * n) * 33,
+              boxes = MKF_HIST_NBUF * (MKF_HIST_TSC * n * n + MKF_HIST_TSM * n) * 32 + 128;
+    return (hist_tma_shape(M, K) && boxes > legacy ? boxes : legacy) + hist_scalar_doubles();
+}
 __host__ __device__ constexpr size_t smem_bytes(int M, int K, bool hist = false, bool collapse = false) {
     return 128 + (size_t)(kBlock / 32) *
                      ((warp_doubles(M, K, hist, collapse) + (hist ? hist_doubles(M, K) : 0)) * sizeof(double) +
@@ -179,7 +221,8 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
 }
 
 template <int M, int K, bool HASR, bool HIST>
-__global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, const __grid_constant__ CUtensorMap ymap) {
+__global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, const __grid_constant__ CUtensorMap ymap,
+                                                            const __grid_constant__ HistMaps<HIST> hmaps) {
     constexpr int N = M + K;
     constexpr int NT = N * (N + 1) / 2;
     constexpr int TT = tile_steps(M, HIST);
@@ -306,43 +349,213 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 #pragma unroll
         for (int c = r; c < N; ++c) P[tri<N>(r, c)] = (r == c) ? 1.0 : 0.0;
 
-    // History mode: the warp transposes its 32 per-thread records through shared memory
-    // ([element][lane], pitch 33: conflict-free writes, 2-way reads) so that every store
+    // History mode.  Legacy path (any shape): the warp transposes its 32 per-thread records through
+    // shared memory ([element][lane], pitch 33: conflict-free writes, 2-way reads) so that every store
     // instruction covers one contiguous 256-byte piece of a model's [n] / [n][n] block.
-    auto emit = [&](double *gmean, double *gcov, int64_t t) {
-        if (!HIST) return;
+    // TMA path (N = 4, 8; hist_tma): every lane writes its OWN record with 16-byte shared-memory stores
+    // into a staging box laid out as the tensor maps' boxes -- covariances {16 doubles, 32 models,
+    // N*N/16 lines} under the 128-byte swizzle, means {N doubles, 32 models} under the N*8-byte swizzle
+    // (both conflict-free for consecutive lanes) -- and lane 0 issues one cp.async.bulk.tensor.3d
+    // shared -> global per array (SASS UTMASTG): no LDS/STG transposition, the store drains while
+    // the next phase computes, rows beyond B are clipped by the tensor map.
+    constexpr bool TST = HIST && hist_tma_shape(M, K);
+    constexpr int kLines = (N * N) / 16;
+    constexpr int TSC = MKF_HIST_TSC, TSM = MKF_HIST_TSM;   // steps per store
+    constexpr unsigned kCovB = (unsigned)kLines * 32u * 128u, kMeanB = 32u * N * 8u;   // one step's records
+    constexpr unsigned kBoxB = TSC * kCovB + TSM * kMeanB;
+    const int htm = HIST ? a.hist_tma : 0;
+    const int tst = TST ? (htm & HIST_TMA_STATE) : 0;
+    const unsigned hbox = (smem_u32(hst) + 1023u) & ~1023u;
+    double *sc_base = hst + (hist_doubles(M, K) - hist_scalar_doubles());
+    const unsigned sbox = (smem_u32(sc_base) + 1023u) & ~1023u;     // sigma box; detf at + 4096, cnt at + 8192
+    double *sc_sigma = sc_base + lane;   // per-lane sector staging: [slot * 32]
+    double *sc_detf = sc_sigma + 128;
+    int *sc_cnt = reinterpret_cast<int *>(sc_base + 256) + lane;
+    auto emit = [&](const int which, int64_t t) {   // which: 0 = predicted, 1 = filtered
+        if constexpr (HIST) {
+            double *gmean = which ? a.fm : a.pm, *gcov = which ? a.fc : a.pc;
+            if constexpr (TST) {
+                const int bit_c = which ? HIST_TMA_FC : HIST_TMA_PC, bit_m = which ? HIST_TMA_FM : HIST_TMA_PM;
+                if (tst & (bit_c | bit_m)) {
+                    const unsigned box = hbox + (MKF_HIST_NBUF > 1 ? (unsigned)which * kBoxB : 0u);
+                    // the store that last read this box must have drained it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(MKF_HIST_NBUF - 1) : "memory");
+                    __syncwarp();
+                    const int uc = (int)(t % TSC), um = (int)(t % TSM);
+                    const bool last = t == a.T - 1;
+                    if (tst & bit_c) {
+                        const unsigned rowb = box + (unsigned)uc * kCovB + (unsigned)lane * 128u, sw = (unsigned)(lane & 7);
 #pragma unroll
-        for (int i = 0; i < N; ++i) hst[i * 33 + lane] = x[i];
+                        for (int e = 0; e < N * N; e += 2) {
+                            const int r = e / N, c = e % N, line = e / 16, ch = (e % 16) / 2;
+                            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowb + (unsigned)line * 4096u +
+                                                                                 (((unsigned)ch ^ sw) << 4)),
+                                         "d"(P[sym<N>(r, c)]), "d"(P[sym<N>(r, c + 1)])
+                                         : "memory");
+                        }
+                    }
+                    if (tst & bit_m) {
+                        const unsigned rowb = box + TSC * kCovB + (unsigned)um * kMeanB + (unsigned)lane * (N * 8u);
+                        const unsigned sw = (N == 8) ? (unsigned)((lane >> 1) & 3) : (unsigned)((lane >> 2) & 1);
 #pragma unroll
-        for (int r = 0; r < N; ++r)
+                        for (int e = 0; e < N; e += 2)
+                            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowb + (((unsigned)(e / 2) ^ sw) << 4)),
+                                         "d"(x[e]), "d"(x[e + 1])
+                                         : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        // a box goes out when its last step is in (or the series ends: the steps beyond T
+                        // are clipped by the tensor map); one bulk group per emit, possibly empty, so
+                        // that "all but the latest group" above always means "the previous use of this box"
+                        if ((tst & bit_c) && (uc == TSC - 1 || last))
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                                             which ? &hmaps.fc : &hmaps.pc),
+                                         "r"(0), "r"((int)b0), "r"((int)(t - uc) * kLines), "r"(box)
+                                         : "memory");
+                        if ((tst & bit_m) && (um == TSM - 1 || last))
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                                             which ? &hmaps.fm : &hmaps.pm),
+                                         "r"(0), "r"((int)b0), "r"((int)(t - um)), "r"(box + TSC * kCovB)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (tst & bit_c) gcov = nullptr;
+                    if (tst & bit_m) gmean = nullptr;
+                }
+            }
+            if (!gcov && !gmean) return;
 #pragma unroll
-            for (int c = 0; c < N; ++c) hst[(N + r * N + c) * 33 + lane] = P[sym<N>(r, c)];
-        __syncwarp();
-        const int rows = (int)min((int64_t)32, a.B - b0);
-        if (gcov) {
-            if (rows == 32) {   // full warp: unrolled so that several LDS/STG pairs are in flight
+            for (int i = 0; i < N; ++i) hst[i * 33 + lane] = x[i];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) hst[(N + r * N + c) * 33 + lane] = P[sym<N>(r, c)];
+            __syncwarp();
+            const int rows = (int)min((int64_t)32, a.B - b0);
+            if (gcov) {
+                if (rows == 32) {   // full warp: unrolled so that several LDS/STG pairs are in flight
 #pragma unroll 8
-                for (int rr = 0; rr < 32; ++rr) {
-                    double *dst = gcov + ((b0 + rr) * a.T + t) * (N * N);
+                    for (int rr = 0; rr < 32; ++rr) {
+                        double *dst = gcov + ((b0 + rr) * a.T + t) * (N * N);
 #pragma unroll
-                    for (int e = lane; e < N * N; e += 32) dst[e] = hst[(N + e) * 33 + rr];
+                        for (int e = lane; e < N * N; e += 32) dst[e] = hst[(N + e) * 33 + rr];
+                    }
+                } else {
+                    for (int rr = 0; rr < rows; ++rr) {
+                        double *dst = gcov + ((b0 + rr) * a.T + t) * (N * N);
+#pragma unroll
+                        for (int e = lane; e < N * N; e += 32) dst[e] = hst[(N + e) * 33 + rr];
+                    }
                 }
-            } else {
-                for (int rr = 0; rr < rows; ++rr) {
-                    double *dst = gcov + ((b0 + rr) * a.T + t) * (N * N);
+            }
+            if (gmean) {
 #pragma unroll
-                    for (int e = lane; e < N * N; e += 32) dst[e] = hst[(N + e) * 33 + rr];
+                for (int idx = lane; idx < 32 * N; idx += 32) {
+                    const int rr = idx / N, e = idx % N;
+                    if (rr < rows) gmean[((b0 + rr) * a.T + t) * N + e] = hst[e * 33 + rr];
+                }
+            }
+            __syncwarp();
+        }
+    };
+    // Step scalars (sigma, detf: f64; cnt: i32) at [b][t]: one value per lane and step, 8 (4) bytes 32
+    // model rows apart -- written directly that is 32 partial sectors per store instruction, and the
+    // read-modify-write traffic it causes costs a quarter of the history kernel's throughput
+    // (tools/ubench_tma_store.cu).  Each lane therefore collects the values of one 32-byte sector
+    // of ITS row in shared memory and writes the sector whole (STG.256) when its last element arrives;
+    // the ragged head and tail of a row (first / last sector not covered completely) go out as scalars.
+    // When the rows allow it (T even / a multiple of 4: 16-byte row pitch) the scalars of 16 steps are
+    // staged as a {16 steps, 32 models} box (128-byte rows under the 128-byte swizzle; cnt: 64-byte rows
+    // under the 64-byte swizzle) and written by one 2-D tensor store per array: whole lines instead of
+    // sectors.  All 32 lanes take part (rows beyond B are clipped).
+    auto put_scalars = [&](int64_t t, double sigma, double detf, int cnt) {
+        if constexpr (HIST) {
+            if (htm & HIST_TMA_SCALARS) {
+                const int u = (int)(t & 15);
+                const bool last = t == a.T - 1;
+                if (u == 0) {
+                    // the boxes' previous store has drained: with state stores in flight it is older than
+                    // the two groups of this step's emits, otherwise it is the latest group
+                    if (lane == 0) {
+                        if (tst) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                }
+                const unsigned o8 = (unsigned)lane * 128u + ((((unsigned)u >> 1) ^ (unsigned)(lane & 7)) << 4) + ((unsigned)u & 1u) * 8u;
+                if (htm & HIST_TMA_SIGMA) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbox + o8), "d"(sigma) : "memory");
+                if (htm & HIST_TMA_DETF) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbox + 4096u + o8), "d"(detf) : "memory");
+                if (htm & HIST_TMA_CNT) {
+                    const unsigned o4 = (unsigned)lane * 64u + ((((unsigned)u >> 2) ^ (unsigned)((lane >> 1) & 3)) << 4) + ((unsigned)u & 3u) * 4u;
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbox + 8192u + o4), "r"(cnt) : "memory");
+                }
+                if (u == 15 || last) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int c0 = (int)(t - u), c1 = (int)b0;
+                        if (htm & HIST_TMA_SIGMA)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&hmaps.sigma),
+                                         "r"(c0), "r"(c1), "r"(sbox)
+                                         : "memory");
+                        if (htm & HIST_TMA_DETF)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&hmaps.detf),
+                                         "r"(c0), "r"(c1), "r"(sbox + 4096u)
+                                         : "memory");
+                        if (htm & HIST_TMA_CNT)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&hmaps.cnt),
+                                         "r"(c0), "r"(c1), "r"(sbox + 8192u)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                return;
+            }
+            if (!active) return;
+            const int64_t o = b * a.T + t;
+            if (!a.hist_vec) {
+                if (a.sigma) a.sigma[o] = sigma;
+                if (a.detf) a.detf[o] = detf;
+                if (a.cnt) a.cnt[o] = cnt;
+                return;
+            }
+            const int s4 = (int)(o & 3), s8 = (int)(o & 7);
+            const bool last = t == a.T - 1;
+            if (a.sigma) sc_sigma[s4 * 32] = sigma;
+            if (a.detf) sc_detf[s4 * 32] = detf;
+            if (a.cnt) sc_cnt[s8 * 32] = cnt;
+            if (s4 == 3 || last) {
+                const int first = (int)max((int64_t)0, (int64_t)s4 - t);   // slots [first, s4] hold steps of this series
+                if (first == 0 && s4 == 3) {
+                    if (a.sigma)
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.sigma + o - 3), "d"(sc_sigma[0]),
+                                     "d"(sc_sigma[32]), "d"(sc_sigma[64]), "d"(sc_sigma[96])
+                                     : "memory");
+                    if (a.detf)
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.detf + o - 3), "d"(sc_detf[0]),
+                                     "d"(sc_detf[32]), "d"(sc_detf[64]), "d"(sc_detf[96])
+                                     : "memory");
+                } else {
+                    for (int s = first; s <= s4; ++s) {
+                        if (a.sigma) a.sigma[o - s4 + s] = sc_sigma[s * 32];
+                        if (a.detf) a.detf[o - s4 + s] = sc_detf[s * 32];
+                    }
+                }
+            }
+            if (a.cnt && (s8 == 7 || last)) {
+                const int first = (int)max((int64_t)0, (int64_t)s8 - t);
+                if (first == 0 && s8 == 7) {
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a.cnt + o - 7),
+                                 "r"(sc_cnt[0]), "r"(sc_cnt[32]), "r"(sc_cnt[64]), "r"(sc_cnt[96]), "r"(sc_cnt[128]),
+                                 "r"(sc_cnt[160]), "r"(sc_cnt[192]), "r"(sc_cnt[224])
+                                 : "memory");
+                } else {
+                    for (int s = first; s <= s8; ++s) a.cnt[o - s8 + s] = sc_cnt[s * 32];
                 }
             }
         }
-        if (gmean) {
-#pragma unroll
-            for (int idx = lane; idx < 32 * N; idx += 32) {
-                const int rr = idx / N, e = idx % N;
-                if (rr < rows) gmean[((b0 + rr) * a.T + t) * N + e] = hst[e * 33 + rr];
-            }
-        }
-        __syncwarp();
     };
 
     KahanSum sum_sigma;
@@ -474,12 +687,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         fprod = __hiloint2double(hi - (ex << 20), __double2loint(fprod));
     };
     auto account = [&](int cnt, double sigma, double stepprod) {
-        if (HIST && active) {
-            const int64_t o = b * a.T + t0 + tt;
-            if (a.sigma) a.sigma[o] = sigma;
-            if (a.detf) a.detf[o] = (cnt > 0) ? log(stepprod) : 0.0;
-            if (a.cnt) a.cnt[o] = cnt;
-        }
+        if (HIST) put_scalars(t0 + tt, sigma, (cnt > 0) ? log(stepprod) : 0.0, cnt);
         // quirk Q4 (kalmanfilter.py:563-566): the first `warmup` OBSERVED steps are
         // dropped from the sums, nobs counts raw steps t >= warmup
         pend_on = (cnt > 0) && (nsig >= a.warmup);
@@ -559,7 +767,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 }
             }
             t_prev = t_cur;
-            emit(a.pm, a.pc, t0 + tt);
+            emit(0, t0 + tt);
 
             // ---- sequential scalar updates (kalmanfilter.py:341-378) -------------------
             if (!warp_any) {
@@ -701,7 +909,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                     }
                 }
             }
-            emit(a.fm, a.fc, t0 + tt);
+            emit(1, t0 + tt);
             account(cnt, sigma, stepprod);
         }
         if (!(COLLAPSE && warp_all)) more = next_step();
@@ -868,6 +1076,10 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
         }
     }
     if (!tma) cp_async_wait<0>();
+    if constexpr (HIST) {
+        // the staging boxes are this CTA's shared memory: the last tensor stores must have read them
+        if (htm && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
 #undef MKF_QQ
 #undef MKF_GG
 
@@ -890,6 +1102,13 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 // Builds the tensor map of y viewed as [rows][row_elems] doubles (defined in filter_dfm.cu).
 int make_y_tensor_map(CUtensorMap *map, const double *y, int64_t rows, int64_t row_elems, int64_t row_stride,
                       int box_rows, int box_elems, int l2_promotion_bytes = 128);
+// Tensor map of a history array [B][T][lines * inner] doubles viewed as dims {inner, B, T * lines}, box
+// {inner, 32, lines * steps}, swizzle span = inner * 8 bytes (32, 64 or 128).  Defined in filter_dfm.cu.
+int make_hist_map(CUtensorMap *map, double *p, int inner, int64_t B, int64_t T, int lines, int steps);
+// Tensor map of a per-step scalar array [B][T] (8-byte doubles or 4-byte integers) viewed as dims {T, B},
+// box {16, 32}, swizzle span = the 16 steps of a row.
+int make_scalar_map(CUtensorMap *map, void *p, int elem_bytes, int64_t B, int64_t T);
+bool hist_tma_enabled();
 // Grow-only device scratch of the hand-off records, one per (device, stream); NULL when the allocation
 // fails (the caller then stays on the single-kernel path).  Defined in filter_dfm.cu.  The transient
 // kernel leaves tnext = T for a warp it finished itself, so sum(T - tnext) counts the warp-steps done

@@ -4,9 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    # transient kernel: plain pivot order vs the default (next pivot's reciprocal started early)
-    "tr_plain": ["-DMKF_PIVOT_AHEAD=0"],
-    "tr_ahead_rcp3": ["-DMKF_RCP3=1"],
+    # history kernel: one staging box shared by the predicted and the filtered record
+    "hist_c1m1": ["-DMKF_HIST_TSC=1", "-DMKF_HIST_TSM=1"],
+    "hist_c1m4": ["-DMKF_HIST_TSC=1", "-DMKF_HIST_TSM=4"],
+    "hist_c2m2": ["-DMKF_HIST_TSC=2", "-DMKF_HIST_TSM=2"],
+    "hist_c2m4": ["-DMKF_HIST_TSC=2", "-DMKF_HIST_TSM=4"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}
