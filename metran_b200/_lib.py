@@ -44,6 +44,7 @@ SIGNATURES = {
     "mkf_project": (ctypes.c_int, [_i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "mkf_dfm_set_handoff": (ctypes.c_int, [ctypes.c_int]),
     "mkf_dfm_set_hist_tma": (ctypes.c_int, [ctypes.c_int]),
+    "mkf_smoother_set_thread_min_batch": (_i64, [_i64]),
     "mkf_release_workspaces": (None, []),
     "mkf_dfm_set_profile": (ctypes.c_int, [ctypes.c_int]),
     "mkf_dfm_last_profile": (ctypes.c_int, [_ptr, _ptr, _ptr]),

@@ -335,6 +335,7 @@ int launch_smoother(SmootherArgs a, cudaStream_t stream) {
 }  // namespace
 
 #include "smoother_wide.cuh"
+#include "smoother_thread.cuh"
 
 namespace {
 
@@ -391,6 +392,10 @@ static int smoother_entry(int64_t B, int64_t T, int32_t n, const double *fm, con
     a.A = A; a.A_stride = A_stride; a.flags = flags; a.sm = sm; a.sc = sc; a.status = status;
     a.p = p; a.Hp = Hp; a.Hp_stride = Hp_stride; a.pmean = proj_mean; a.pvar = proj_var; a.svar = state_var;
     cudaStream_t s = (cudaStream_t)stream;
+    if (p == 0 && (n == 4 || n == 8)) {     // big batches of small diagonal-A models: one thread per model
+        const int rc = launch_smoother_thread(a, s);
+        if (rc != MKF_ERR_UNSUPPORTED) return rc;
+    }
     if (n <= 4) return launch_smoother<4>(a, s);
     if (n <= 8) return launch_smoother<8>(a, s);
     if (n <= 16) return launch_smoother<16>(a, s);
@@ -399,6 +404,10 @@ static int smoother_entry(int64_t B, int64_t T, int32_t n, const double *fm, con
 #endif
     if (MKF_SMOOTHER_WIDE) return launch_smoother_wide(a, s);      // four warps per model (smoother_wide.cuh)
     return launch_smoother<32>(a, s);
+}
+
+extern "C" int64_t mkf_smoother_set_thread_min_batch(int64_t min_batch) {
+    return (int64_t)g_smt_min_b.exchange(min_batch < 0 ? (long long)MKF_SMT_MIN_B : (long long)min_batch);
 }
 
 extern "C" int mkf_smoother(int64_t B, int64_t T, int32_t n, const double *fm, const double *fc,

@@ -207,6 +207,9 @@ class FakeLib:
     def mkf_dfm_set_hist_tma(self, enabled):
         return 1
 
+    def mkf_smoother_set_thread_min_batch(self, min_batch):
+        return 2048
+
     # ---- smoother / projections / reduction ---------------------------------------------
     def mkf_smoother(self, B, T, n, fm, fc, pm, pc, A, As, flags, sm, sc, status, stream):
         self.calls.append(("mkf_smoother", B, T, n))

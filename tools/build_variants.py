@@ -4,11 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    # history kernel: one staging box shared by the predicted and the filtered record
-    "hist_c1m1": ["-DMKF_HIST_TSC=1", "-DMKF_HIST_TSM=1"],
-    "hist_c1m4": ["-DMKF_HIST_TSC=1", "-DMKF_HIST_TSM=4"],
-    "hist_c2m2": ["-DMKF_HIST_TSC=2", "-DMKF_HIST_TSM=2"],
-    "hist_c2m4": ["-DMKF_HIST_TSC=2", "-DMKF_HIST_TSM=4"],
+    # steady kernel: deeper ring (for small batches, where the warp waits for its own loads)
+    "st_s6": ["-DMKF_ST_STAGES=6"],
+    "st_s9": ["-DMKF_ST_STAGES=9"],
+    # transient kernel: deeper ring
+    "tr_s3": ["-DMKF_STAGES=3"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}
