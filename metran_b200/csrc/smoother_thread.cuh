@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <type_traits>
 
 namespace mkf_dfm {
 int make_hist_map(CUtensorMap *map, double *p, int inner, int64_t B, int64_t T, int lines, int steps);
@@ -62,17 +63,36 @@ struct SmtLayout {
     static constexpr unsigned TOTAL = BARS + 64u;
 };
 
+template <int I, int E, class F>
+__device__ __forceinline__ void smt_static_for(F &&f) {
+    if constexpr (I < E) {
+        f(std::integral_constant<int, I>{});
+        smt_static_for<I + 1, E>(f);
+    }
+}
+
+#ifndef MKF_SMT_WARPS
+#define MKF_SMT_WARPS 2      // warps that share one set of boxes (32 models): row c of the step goes to warp c % NW
+#endif
+
 template <int N>
-__global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherArgs a, const __grid_constant__ SmThreadMaps maps) {
+__global__ void __launch_bounds__(32 * MKF_SMT_WARPS, 2) smoother_thread_kernel(const SmootherArgs a, const __grid_constant__ SmThreadMaps maps) {
     using LY = SmtLayout<N>;
     constexpr int NT = N * (N + 1) / 2;
+    constexpr int NW = MKF_SMT_WARPS;
+    static_assert(N % NW == 0, "rows must divide among the warps");
     extern __shared__ unsigned char smt_raw[];
     const unsigned base = (smem_u32(smt_raw) + 1023u) & ~1023u;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool leader = threadIdx.x == 0;          // issues every TMA operation of the CTA
     const int64_t b0 = (int64_t)blockIdx.x * 32, b = b0 + lane;
     const bool active = b < a.B;
     const int64_t T = a.T;
     const unsigned bar_pc = base + LY::BARS, bar_st0 = bar_pc + 8, bar_st1 = bar_pc + 16;
+    auto cta_sync = [&]() {
+        if (NW == 1) __syncwarp();
+        else __syncthreads();
+    };
 
     // ---- addressing inside the swizzled boxes -------------------------------------------------
     // covariance element (r, c): line (r*N + c) / 16, 16-byte chunk ((r*N + c) % 16) / 2 ^ (lane & 7)
@@ -139,24 +159,24 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
         load3d(base + LY::PC, &maps.pc, (int)(t + 1) * LY::LINES, bar_pc);
     };
 
-    if (lane == 0) {
+    if (leader) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_pc) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_st0) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_st1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    __syncwarp();
     // diag(A) of this lane's model: [i][lane]
-    {
+    if (w == 0) {
         const double *Ab = a.A + (active ? b : b0) * a.A_stride;
 #pragma unroll
         for (int i = 0; i < N; ++i) sts1(base + LY::AD + (unsigned)(i * 32 + lane) * 8u, Ab[i * N + i]);
     }
+    cta_sync();
 
     // ---- t = T - 1: smoothed = filtered (kalmanfilter.py:450-451) ---------------------------------
     // P_f[T-1] and x_f[T-1] are fetched as "stage T-1" (the x_p box of that stage is not used)
     unsigned ph_pc = 0, ph_st0 = 0, ph_st1 = 0;
-    if (lane == 0) {
+    if (leader) {
         const unsigned s = (unsigned)((T - 1) & 1), bar = s ? bar_st1 : bar_st0;
         expect(bar, LY::COV + LY::MEAN);
         load3d(base + (s ? LY::FC1 : LY::FC0), &maps.fc, (int)(T - 1) * LY::LINES, bar);
@@ -166,7 +186,6 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
             issue_pc(T - 2);
         }
     }
-    double xs[N];   // x_s[t+1]
     {
         const unsigned s = (unsigned)((T - 1) & 1);
         bar_wait(s ? bar_st1 : bar_st0, 0u);
@@ -174,21 +193,26 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
         const unsigned fcb = base + (s ? LY::FC1 : LY::FC0), fmb = base + (s ? LY::FM1 : LY::FM0);
 #pragma unroll
         for (int r = 0; r < N; ++r)
+            if (r % NW == w) {
 #pragma unroll
-            for (int c = 0; c < N; c += 2) {
-                double v0, v1;
-                lds2(cov_pair(fcb, r, c), v0, v1);
-                sts2(cov_pair(base + LY::SC, r, c), v0, v1);
+                for (int c = 0; c < N; c += 2) {
+                    double v0, v1;
+                    lds2(cov_pair(fcb, r, c), v0, v1);
+                    sts2(cov_pair(base + LY::SC, r, c), v0, v1);
+                }
             }
-        const unsigned slot = base + LY::SMO + (unsigned)((T - 1) % kSmtTSM) * LY::MEAN;
+        if (w == 0) {
+            const unsigned slot = base + LY::SMO + (unsigned)((T - 1) % kSmtTSM) * LY::MEAN;
 #pragma unroll
-        for (int i = 0; i < N; i += 2) {
-            lds2(vec_pair(fmb, i), xs[i], xs[i + 1]);
-            sts2(vec_pair(slot, i), xs[i], xs[i + 1]);
+            for (int i = 0; i < N; i += 2) {
+                double v0, v1;
+                lds2(vec_pair(fmb, i), v0, v1);
+                sts2(vec_pair(slot, i), v0, v1);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
+        cta_sync();
+        if (leader) {
             store3d(&maps.sc, (int)(T - 1) * LY::LINES, base + LY::SC);
             if ((T - 1) % kSmtTSM == 0) store3d(&maps.sm, (int)(T - 1), base + LY::SMO);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -199,10 +223,10 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
     for (int64_t t = T - 2; t >= 0; --t) {
         const unsigned s = (unsigned)(t & 1);
         // stage (t - 1) & 1 == (t + 1) & 1 was read by step t + 1 (or by the prologue), which has finished
-        // -- proxy fence and warp barrier in front of its stores: refill it for step t - 1
-        if (lane == 0 && t >= 1) issue_stage(t - 1);
+        // -- proxy fence and barrier in front of its stores: refill it for step t - 1
+        if (leader && t >= 1) issue_stage(t - 1);
 
-        // ---- P_p[t+1] -> registers; D = P_s[t+1] - P_p[t+1]; Cholesky --------------------------------
+        // ---- P_p[t+1] -> registers; D = P_s[t+1] - P_p[t+1] (every warp: all of it) --------------------
         bar_wait(bar_pc, ph_pc);
         ph_pc ^= 1u;
         double L[NT], D[NT];   // packed lower triangle, (r, c), c <= r: index r(r+1)/2 + c
@@ -220,21 +244,28 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
                     D[r * (r + 1) / 2 + c + 1] = s1 - p1;
                 }
             }
-        // the P_p box is free: fetch the next step's matrix while this step computes
+        // x_s[t+1]: the previous step left it in its slot of the output box
+        double xs[N];
+        {
+            const unsigned prev = base + LY::SMO + (unsigned)((t + 1) % kSmtTSM) * LY::MEAN;
+#pragma unroll
+            for (int i = 0; i < N; i += 2) lds2(vec_pair(prev, i), xs[i], xs[i + 1]);
+        }
+        // the P_p box is free (and nobody reads the old P_s any more): fetch the next step's matrix while
+        // this step computes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0 && t >= 1) issue_pc(t - 1);
+        cta_sync();
+        if (leader && t >= 1) issue_pc(t - 1);
 
-        double dmax = 0.0, inv[N];
+        // ---- Cholesky of P_p (in place); a pivot that is not positive relative to its original diagonal entry
+        // belongs to a direction in which P_p is numerically singular: zero gain there, as the reference's pinv
+        // (kalmanfilter.py:455) -- the rule of smoother_kernel
+        double dmax = 0.0, inv[N], d0[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) dmax = fmax(dmax, L[j * (j + 1) / 2 + j]);
-        // a pivot that is not positive relative to its original diagonal entry belongs to a direction in which
-        // P_p is numerically singular: zero gain there, as the reference's pinv (kalmanfilter.py:455) -- the
-        // rule of smoother_kernel
-        // right-looking Cholesky, in place; the original diagonal entries are needed by the pivot test
-        double d0[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) d0[j] = L[j * (j + 1) / 2 + j];
+        for (int j = 0; j < N; ++j) {
+            d0[j] = L[j * (j + 1) / 2 + j];
+            dmax = fmax(dmax, d0[j]);
+        }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             const double pjj = L[j * (j + 1) / 2 + j];
@@ -242,7 +273,6 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
             if (!okp) status |= MKF_STATUS_CHOL_FAILED;
             const double iv = okp ? rsqrt(pjj) : 0.0;
             inv[j] = iv;
-            L[j * (j + 1) / 2 + j] = pjj * iv;
 #pragma unroll
             for (int r = j + 1; r < N; ++r) L[r * (r + 1) / 2 + j] *= iv;
 #pragma unroll
@@ -251,12 +281,10 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
                 for (int c = j + 1; c <= r; ++c)
                     L[r * (r + 1) / 2 + c] = fma(-L[r * (r + 1) / 2 + j], L[c * (c + 1) / 2 + j], L[r * (r + 1) / 2 + c]);
         }
-
-        // ---- P_p^-1 = L^-T L^-1 explicitly: the eight solves (L L^T) g = (A P_f)[:, c] become matrix-vector
-        // products with eight independent accumulators each instead of 16 dependent substitution steps
-        // (the step is latency-bound otherwise: one warp per SM sub-partition).  W = L^-1 in place, column by
-        // column; a rejected pivot (inv = 0) leaves its row and column of W, hence of P_p^-1, zero: zero gain
-        // in that direction, as before.
+        // ---- P_p^-1 = L^-T L^-1 explicitly: the n solves (L L^T) g = (A P_f)[:, c] become matrix-vector
+        // products with n independent accumulators each instead of 2n dependent substitution steps.  W = L^-1
+        // in place, column by column; a rejected pivot (inv = 0) leaves its row and column of W, hence of
+        // P_p^-1, zero: zero gain in that direction, as before.
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             L[j * (j + 1) / 2 + j] = inv[j];
@@ -292,24 +320,19 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
             delta[i] = xs[i] - p0;
             delta[i + 1] = xs[i + 1] - p1;
         }
-        // the box of P_s is about to be rewritten: its store (issued at the end of the previous step) must
-        // have read it, and so must the store of the x_s box when this step starts a new one
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
         const unsigned slot = base + LY::SMO + (unsigned)(t % kSmtTSM) * LY::MEAN;
 
-        // ---- row by row: G[c] = solve, x_s[c], M[c] = G[c] D, P_s[c][j <= c] ---------------------------
-#pragma unroll
-        for (int c = 0; c < N; ++c) {
+        // ---- rows c = NW * round + w: G[c] = (A P_f)[:, c]^T P_p^-1, x_s[c], M[c] = G[c] D, P_s[c][j <= c] ----
+        smt_static_for<0, N / NW>([&](auto rdc) {
+            constexpr int RD = decltype(rdc)::value;
             double pf[N], g[N];
+            auto row_body = [&](auto cc) {
+                constexpr int C = decltype(cc)::value;
 #pragma unroll
-            for (int i = 0; i < N; i += 2) lds2(cov_pair(fcb, c, i), pf[i], pf[i + 1]);   // row c of P_f (= column c)
-#pragma unroll
-            for (int i = 0; i < N; ++i) g[i] = pf[i] * lds1(base + LY::AD + (unsigned)(i * 32 + lane) * 8u);   // (A P_f)[:, c]
-            {
+                for (int i = 0; i < N; i += 2) lds2(cov_pair(fcb, C, i), pf[i], pf[i + 1]);   // row C of P_f (= column C)
                 double z[N];
 #pragma unroll
-                for (int i = 0; i < N; ++i) z[i] = g[i];
+                for (int i = 0; i < N; ++i) z[i] = pf[i] * lds1(base + LY::AD + (unsigned)(i * 32 + lane) * 8u);   // (A P_f)[:, C]
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     double acc = 0.0;
@@ -320,67 +343,83 @@ __global__ void __launch_bounds__(32, 2) smoother_thread_kernel(const SmootherAr
                     }
                     g[i] = acc;
                 }
-            }
 #pragma unroll
-            for (int i = 0; i < N; i += 2) sts2(vec_pair(base + LY::G + (unsigned)c * LY::MEAN, i), g[i], g[i + 1]);
-            // x_s[t][c] = x_f[c] + G[c] . delta
-            double xn = lds1(vec_pair(fmb, c & ~1) + (unsigned)(c & 1) * 8u);
+                for (int i = 0; i < N; i += 2) sts2(vec_pair(base + LY::G + (unsigned)C * LY::MEAN, i), g[i], g[i + 1]);
+            };
+            auto row_tail = [&](auto cc) {
+                constexpr int C = decltype(cc)::value;
+                // x_s[t][C] = x_f[C] + G[C] . delta
+                double xn = lds1(vec_pair(fmb, C & ~1) + (unsigned)(C & 1) * 8u);
 #pragma unroll
-            for (int i = 0; i < N; ++i) xn = fma(g[i], delta[i], xn);
-            xs[c] = xn;   // (x_s[t+1][c] is not needed any more: delta holds the difference)
-            // M[c] = G[c] D
-            double mrow[N];
+                for (int i = 0; i < N; ++i) xn = fma(g[i], delta[i], xn);
+                sts1(vec_pair(slot, C & ~1) + (unsigned)(C & 1) * 8u, xn);
+                // M[C] = G[C] D
+                double mrow[N];
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                double acc = 0.0;
+                for (int j = 0; j < N; ++j) {
+                    double acc = 0.0;
 #pragma unroll
-                for (int k2 = 0; k2 < N; ++k2) {
-                    const int hi = k2 > j ? k2 : j, lo = k2 > j ? j : k2;
-                    acc = fma(g[k2], D[hi * (hi + 1) / 2 + lo], acc);
+                    for (int k2 = 0; k2 < N; ++k2) {
+                        const int hi = k2 > j ? k2 : j, lo = k2 > j ? j : k2;
+                        acc = fma(g[k2], D[hi * (hi + 1) / 2 + lo], acc);
+                    }
+                    mrow[j] = acc;
                 }
-                mrow[j] = acc;
-            }
-            // P_s[t][c][j] = P_f[c][j] + M[c] . G[j], j <= c; mirrored to (j, c)
-            double prow[N];
+                // P_s[t][C][j] = P_f[C][j] + M[C] . G[j], j <= C; mirrored to (j, C)
+                double prow[N];
 #pragma unroll
-            for (int j = 0; j <= c; ++j) {
-                double gj[N];
-                if (j < c) {
+                for (int j = 0; j <= C; ++j) {
+                    double gj[N];
+                    if (j < C) {
 #pragma unroll
-                    for (int i = 0; i < N; i += 2) lds2(vec_pair(base + LY::G + (unsigned)j * LY::MEAN, i), gj[i], gj[i + 1]);
-                } else {
+                        for (int i = 0; i < N; i += 2) lds2(vec_pair(base + LY::G + (unsigned)j * LY::MEAN, i), gj[i], gj[i + 1]);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) gj[i] = g[i];
+                        for (int i = 0; i < N; ++i) gj[i] = g[i];
+                    }
+                    double s0 = pf[j], s1 = 0.0;
+#pragma unroll
+                    for (int k2 = 0; k2 < N; k2 += 2) {
+                        s0 = fma(mrow[k2], gj[k2], s0);
+                        s1 = fma(mrow[k2 + 1], gj[k2 + 1], s1);
+                    }
+                    prow[j] = s0 + s1;
                 }
-                double s0 = pf[j], s1 = 0.0;
 #pragma unroll
-                for (int k2 = 0; k2 < N; k2 += 2) {
-                    s0 = fma(mrow[k2], gj[k2], s0);
-                    s1 = fma(mrow[k2 + 1], gj[k2 + 1], s1);
+                for (int j = 0; j <= C; j += 2) {
+                    if (j + 1 <= C) sts2(cov_pair(base + LY::SC, C, j), prow[j], prow[j + 1]);
+                    else sts1(cov_pair(base + LY::SC, C, j), prow[j]);                       // (C, C) with C even: first half of its pair
                 }
-                prow[j] = s0 + s1;
-            }
 #pragma unroll
-            for (int j = 0; j <= c; j += 2) {
-                if (j + 1 <= c) sts2(cov_pair(base + LY::SC, c, j), prow[j], prow[j + 1]);
-                else sts1(cov_pair(base + LY::SC, c, j), prow[j]);                       // (c, c) with c even: first half of its pair
-            }
-#pragma unroll
-            for (int j = 0; j < c; ++j) sts1(cov_pair(base + LY::SC, j, c & ~1) + (unsigned)(c & 1) * 8u, prow[j]);   // mirror (j, c)
-        }
-#pragma unroll
-        for (int i = 0; i < N; i += 2) sts2(vec_pair(slot, i), xs[i], xs[i + 1]);
+                for (int j = 0; j < C; ++j) sts1(cov_pair(base + LY::SC, j, C & ~1) + (unsigned)(C & 1) * 8u, prow[j]);   // mirror (j, C)
+            };
+            // the row index decides register indices and addresses: one unrolled copy per (round, warp)
+#define MKF_SMT_ROW(FN)                                                                   \
+            do {                                                                          \
+                if (NW == 1 || w == 0) FN(std::integral_constant<int, RD * NW>{});        \
+                else if (NW >= 2 && w == 1) FN(std::integral_constant<int, (RD * NW + 1) % N>{}); \
+                else if (NW >= 4 && w == 2) FN(std::integral_constant<int, (RD * NW + 2) % N>{}); \
+                else FN(std::integral_constant<int, (RD * NW + 3) % N>{});                \
+            } while (0)
+            MKF_SMT_ROW(row_body);
+            // the box of P_s is about to be rewritten: its store (issued at the end of the previous step) must
+            // have read it, and so must the store of the x_s box when this step starts a new one
+            if (RD == 0 && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            cta_sync();     // G rows of this round visible to every warp; (round 0) the boxes are free
+            MKF_SMT_ROW(row_tail);
+#undef MKF_SMT_ROW
+        });
 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
+        cta_sync();
+        if (leader) {
             store3d(&maps.sc, (int)t * LY::LINES, base + LY::SC);
             if (t % kSmtTSM == 0) store3d(&maps.sm, (int)t, base + LY::SMO);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    if (active && a.status) a.status[b] = status;
+    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (w == 0 && active && a.status) a.status[b] = status;
 }
 
 // Returns MKF_ERR_UNSUPPORTED when the call is not this kernel's (the caller then takes smoother_kernel).
@@ -407,7 +446,7 @@ int launch_smoother_thread_n(const SmootherArgs &a, cudaStream_t stream) {
         return MKF_ERR_CUDA;
     }
     const int64_t blocks = (a.B + 31) / 32;
-    kern<<<(unsigned)blocks, 32, smem, stream>>>(a, maps);
+    kern<<<(unsigned)blocks, 32 * MKF_SMT_WARPS, smem, stream>>>(a, maps);
     return mkf_host::check_launch();
 }
 

@@ -4,17 +4,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    # steady kernel: deeper ring (for small batches, where the warp waits for its own loads)
-    "st_s6": ["-DMKF_ST_STAGES=6"],
-    "st_s9": ["-DMKF_ST_STAGES=9"],
-    # transient kernel: deeper ring
-    "tr_s3": ["-DMKF_STAGES=3"],
+    # thread-per-model smoother: warps that share one set of boxes
+    "smt_w1": ["-DMKF_SMT_WARPS=1"],
+    "smt_w4": ["-DMKF_SMT_WARPS=4"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}
 out = os.path.join(ROOT, "metran_b200", "lib", "variants")
 os.makedirs(out, exist_ok=True)
-srcs = ["api.cu", "filter_dfm.cu", "filter_dfm_k0.cu", "filter_dfm_k1.cu", "filter_dfm_k2.cu", "filter_dfm_k3.cu"]
+srcs = list(build.SOURCES)
 for name, flags in VARIANTS.items():
     objs = []
     for s in srcs:

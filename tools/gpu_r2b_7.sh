@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_smoother_thread.py -m gpu -x -q 2>&1 | tail -15
+timeout 300 python tools/profile_smoother8.py 37888 96 metran_b200/lib/variants/lib_smt_w1.so metran_b200/lib/variants/lib_smt_w4.so 2>&1 | tail -6 | tee gpurun_out/r02o_smoother8.txt
+timeout 300 python tools/profile_smoother8.py 8192 500 metran_b200/lib/variants/lib_smt_w4.so 2>&1 | tail -4 | tee -a gpurun_out/r02o_smoother8.txt
