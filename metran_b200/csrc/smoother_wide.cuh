@@ -9,13 +9,11 @@
 // Here 128 threads share the step.  Thread (w, l): warp w = 0..3, lane l.
 //   0. P_p[t+1], P_f[t] arrive by cp.async (issued one step ahead) and are spread into padded
 //      shared-memory matrices; D = P_s[t+1] - P_p[t+1].
-//   1. Blocked Cholesky of P_p in shared memory, 4 panels of 8 columns: every thread factorises
-//      the 8 x 8 diagonal block redundantly in registers (8 dependent pivots, the only serial
-//      part), warp 0 solves the panel rows below it, all threads update the trailing matrix
-//      (three block barriers per panel).
-//   2. Substitutions  (L L^T) g_c = (A P_f)[:, c]: column c is owned by FOUR adjacent lanes that
-//      hold rows q, q+4, ... of it; the solved entry of step k is passed among the four by one
-//      shuffle.  32 columns x 4 lanes = 128 threads, no block barrier inside.
+//   1. P_p^-1 in place by Gauss-Jordan elimination without pivoting: thread (w, l) keeps its 8 entries
+//      of row l in registers, column k and row k of the current matrix travel through two small
+//      double-buffered vectors -- one block barrier and 8 FMAs per thread and pivot (round 2; the
+//      blocked Cholesky + 64-step substitutions of the first version took three times as long).
+//   2. G = (A P_f)^T P_p^-1 as a 32 x 32 x 32 product with the operands in shared memory.
 //   3. x_s[t], M = G D, P_s[t] = P_f + M G^T: thread (w, l) produces row l, columns [8w, 8w+8).
 #pragma once
 
@@ -39,10 +37,12 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     double *sM = sm_;    sm_ += NP * LD;   // G D
     double *sPs = sm_;   sm_ += NP * LD;   // P_s[t+1], carried between steps
     double *sdel = sm_;  sm_ += NP;        // x_s[t+1] - x_p[t+1]
-    double *sinv = sm_;  sm_ += NP;        // 1 / L_ii
     double *sa = sm_;    sm_ += NP;        // diag(A)
     double *sxs = sm_;   sm_ += NP;        // x_s[t]
     double *sdg = sm_;   sm_ += NP;        // original diagonal of P_p[t+1] (singularity test of the pivots)
+    double *scol = sm_;  sm_ += 2 * NP;    // Gauss-Jordan: column k of the current matrix (double-buffered)
+    double *srow = sm_;  sm_ += 2 * NP;    // ... and its row k
+    double *spart = sm_; sm_ += 4 * NP;    // partial sums of G delta, one per warp
     double *stage = sm_; sm_ += 2 * 2 * NP * NP;   // [buffer][P_p | P_f][n*n] as they lie in global memory
     double *sHp = sm_;   sm_ += (size_t)a.p * NP;  // projection matrix rows (fused epilogue)
     double *sA = sm_;                      // full A (only when not diagonal)
@@ -142,151 +142,98 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         }
         __syncthreads();
 
-        // ---- 1. blocked Cholesky P_p = L L^T in sL (lower triangle) -----------------------------
+        // ---- 1. P_p^-1 in place: Gauss-Jordan elimination without pivoting (P_p is symmetric positive
+        // definite; the pivots are the squares of the Cholesky pivots, so the singularity rule of
+        // smoother.cu carries over unchanged).  Thread (w, l) keeps its 8 entries of row l in registers
+        // for all 32 pivots; per pivot only column k (from the warp that owns it) and row k (from lane k of
+        // every warp) are published through two small double-buffered vectors: ONE block barrier per
+        // pivot, 8 FMAs per thread, no triangular solves afterwards -- the blocked Cholesky with its
+        // redundant 8 x 8 factorisations, three barriers per panel and 64 dependent substitution steps per
+        // right-hand side (four lanes per column, a shuffle per step) cost three times as much.
         double dmax = 0.0;                        // largest diagonal entry: scale of pinv's cut-off
         for (int i = 0; i < n; ++i) dmax = fmax(dmax, sdg[i]);
-#pragma unroll 1
-        for (int p = 0; p < NP / PW; ++p) {
-            const int j0 = p * PW;
-            // diagonal block, redundantly in every thread
-            double Ld[PW * (PW + 1) / 2], inv[PW];
-            {
-                int e = 0;
+        double pr[PW];
 #pragma unroll
-                for (int i = 0; i < PW; ++i)
+        for (int c = 0; c < PW; ++c) pr[c] = sL[l * LD + c0 + c];
 #pragma unroll
-                    for (int j = 0; j <= i; ++j) Ld[e++] = sL[(j0 + i) * LD + j0 + j];
-            }
-            auto lt = [](int i, int j) { return i * (i + 1) / 2 + j; };       // j <= i
-            __syncthreads();      // every thread has the block in registers before warp 0 overwrites it
+        for (int k = 0; k < NP; ++k) {
+            double *colk = scol + (k & 1) * NP, *rowk = srow + (k & 1) * NP;
+            if (w == k / PW) colk[l] = pr[k % PW];
+            if (l == k) {
 #pragma unroll
-            for (int j = 0; j < PW; ++j) {
-                const double pjj = Ld[lt(j, j)];
-                // numerically singular direction: zero gain, as the reference's pinv (see smoother.cu)
-                const bool okp = pjj > 1.5e-14 * sdg[j0 + j] && pjj > 1e-15 * dmax && pjj > 0.0;
-                if (!okp) status |= MKF_STATUS_CHOL_FAILED;
-                const double iv = okp ? rsqrt(pjj) : 0.0;
-                inv[j] = iv;
-                Ld[lt(j, j)] = pjj * iv;
-#pragma unroll
-                for (int i = j + 1; i < PW; ++i) Ld[lt(i, j)] *= iv;
-#pragma unroll
-                for (int i = j + 1; i < PW; ++i)
-#pragma unroll
-                    for (int k = j + 1; k <= i; ++k) Ld[lt(i, k)] = fma(-Ld[lt(i, j)], Ld[lt(k, j)], Ld[lt(i, k)]);
-            }
-            // warp 0: rows of the diagonal block and the panel rows below it
-            if (w == 0) {
-                if (l >= j0 && l < j0 + PW) {
-                    const int i = l - j0;
-#pragma unroll
-                    for (int j = 0; j < PW; ++j) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int ii = 0; ii < PW; ++ii)
-                            if (ii == i && j <= ii) v = Ld[lt(ii, j)];
-                        sL[l * LD + j0 + j] = v;
-                    }
-                } else if (l >= j0 + PW) {
-                    // row l of the panel: solve x Ld^T = A[l][j0..j0+8)
-                    double xr[PW];
-#pragma unroll
-                    for (int j = 0; j < PW; ++j) xr[j] = sL[l * LD + j0 + j];
-#pragma unroll
-                    for (int j = 0; j < PW; ++j) {
-                        xr[j] *= inv[j];
-#pragma unroll
-                        for (int k = j + 1; k < PW; ++k) xr[k] = fma(-xr[j], Ld[lt(k, j)], xr[k]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < PW; ++j) sL[l * LD + j0 + j] = xr[j];
-                }
-#pragma unroll
-                for (int j = 0; j < PW; ++j)
-                    if (l == j) sinv[j0 + j] = inv[j];
+                for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2 *>(rowk + c0 + c) = make_double2(pr[c], pr[c + 1]);
             }
             __syncthreads();
-            // trailing update: A[r][c] -= sum_k L[r][j0+k] L[c][j0+k], rows/cols beyond the panel
-            if (l >= j0 + PW && c0 >= j0 + PW) {
-                double lr[PW];
+            const double d = rowk[k];
+            // numerically singular direction: zero gain, as the reference's pinv (see smoother.cu)
+            const bool okp = d > 1.5e-14 * sdg[k] && d > 1e-15 * dmax && d > 0.0;
+            if (!okp) status |= MKF_STATUS_CHOL_FAILED;
+            const double pv = okp ? rcp_nr(d) : 0.0;
+            const double cl = colk[l];
 #pragma unroll
-                for (int k = 0; k < PW; ++k) lr[k] = sL[l * LD + j0 + k];
+            for (int c = 0; c < PW; c += 2) {
+                const double2 rk2 = *reinterpret_cast<const double2 *>(rowk + c0 + c);
+                const double rk[2] = {rk2.x * pv, rk2.y * pv};
 #pragma unroll
-                for (int c = 0; c < PW; ++c) {
-                    const int cc = c0 + c;
-                    double acc = sL[l * LD + cc];
-#pragma unroll
-                    for (int k = 0; k < PW; k += 2) {
-                        const double2 lc = *reinterpret_cast<const double2 *>(sL + cc * LD + j0 + k);
-                        acc = fma(-lr[k], lc.x, acc);
-                        acc = fma(-lr[k + 1], lc.y, acc);
-                    }
-                    sL[l * LD + cc] = acc;       // (entries above the diagonal are never read)
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- 2. column c of G^T: (L L^T) g = (A P_f)[:, c]; four lanes per column -------------
-        const int col = w * PW + (l >> 2), q = l & 3;
-        double z[NP / 4];                         // rows q, q + 4, ..., q + 28 of the column
-        if (diagA) {
-#pragma unroll
-            for (int j = 0; j < NP / 4; ++j) z[j] = sa[q + 4 * j] * sPf[(q + 4 * j) * LD + col];
-        } else {
-#pragma unroll
-            for (int j = 0; j < NP / 4; ++j) {
-                double s = 0.0;
-                for (int k = 0; k < n; ++k) s = fma(sA[(q + 4 * j) * LD + k], sPf[k * LD + col], s);
-                z[j] = s;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {            // forward substitution with L
-            const double mine = z[k >> 2] * sinv[k];
-            const double zk = __shfl_sync(0xffffffffu, mine, (l & ~3) | (k & 3));
-            if (q == (k & 3)) z[k >> 2] = zk;
-#pragma unroll
-            for (int j = 0; j < NP / 4; ++j) {
-                const int i = q + 4 * j;
-                if (4 * j + 3 > k) {              // some lane of the group has a row below k here
-                    const double lik = sL[i * LD + k];
-                    if (i > k) z[j] = fma(-lik, zk, z[j]);
+                for (int h = 0; h < 2; ++h) {
+                    const int j = c0 + c + h;
+                    const double upd = (j == k) ? -cl * pv : fma(-cl, rk[h], pr[c + h]);
+                    const double own = (j == k) ? pv : rk[h];
+                    pr[c + h] = (l == k) ? own : upd;
                 }
             }
         }
 #pragma unroll
-        for (int k = NP - 1; k >= 0; --k) {       // backward substitution with L^T
-            const double mine = z[k >> 2] * sinv[k];
-            const double zk = __shfl_sync(0xffffffffu, mine, (l & ~3) | (k & 3));
-            if (q == (k & 3)) z[k >> 2] = zk;
+        for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2 *>(sL + l * LD + c0 + c) = make_double2(pr[c], pr[c + 1]);
+        if (!diagA) {
+            // F = A P_f (row l, columns c0..c0+7) into sM; it is consumed before step 3 rewrites sM
+            double fr[PW];
 #pragma unroll
-            for (int j = 0; j < NP / 4; ++j) {
-                const int i = q + 4 * j;
-                if (4 * j < k) {
-                    const double lki = sL[k * LD + i];
-                    if (i < k) z[j] = fma(-lki, zk, z[j]);
+            for (int c = 0; c < PW; ++c) fr[c] = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double av = sA[l * LD + k];
+#pragma unroll
+                for (int c = 0; c < PW; c += 2) {
+                    const double2 pf = *reinterpret_cast<const double2 *>(sPf + k * LD + c0 + c);
+                    fr[c] = fma(av, pf.x, fr[c]);
+                    fr[c + 1] = fma(av, pf.y, fr[c + 1]);
                 }
             }
-        }
-        // z = row `col` of G at columns q + 4j; x_s[t][col] = x_f + G[col][:] . delta
-        {
-            double part = 0.0;
 #pragma unroll
-            for (int j = 0; j < NP / 4; ++j) {
-                sG[col * LD + q + 4 * j] = z[j];
-                part = fma(z[j], sdel[q + 4 * j], part);
-            }
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (q == 0) {
-                const double xf = (col < n) ? a.fm[(base + t) * n + col] : 0.0;
-                const double xn = xf + part;
-                sxs[col] = xn;                     // read again only after the next barriers
-                if (col < n) a.sm[(base + t) * n + col] = xn;
-            }
+            for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2 *>(sM + l * LD + c0 + c) = make_double2(fr[c], fr[c + 1]);
         }
         __syncthreads();
+
+        // ---- 2. G = (A P_f)^T P_p^-1: row l, columns c0..c0+7; x_s[t] = x_f + G delta --------------------
+        {
+            double g[PW];
+#pragma unroll
+            for (int c = 0; c < PW; ++c) g[c] = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double f = diagA ? sa[k] * sPf[k * LD + l] : sM[k * LD + l];
+#pragma unroll
+                for (int c = 0; c < PW; c += 2) {
+                    const double2 pi = *reinterpret_cast<const double2 *>(sL + k * LD + c0 + c);
+                    g[c] = fma(f, pi.x, g[c]);
+                    g[c + 1] = fma(f, pi.y, g[c + 1]);
+                }
+            }
+            double part = 0.0;
+#pragma unroll
+            for (int c = 0; c < PW; c += 2) {
+                *reinterpret_cast<double2 *>(sG + l * LD + c0 + c) = make_double2(g[c], g[c + 1]);
+                part = fma(g[c], sdel[c0 + c], part);
+                part = fma(g[c + 1], sdel[c0 + c + 1], part);
+            }
+            spart[w * NP + l] = part;
+        }
+        __syncthreads();
+        if (tid < NP) {
+            const double xf = (tid < n) ? a.fm[(base + t) * n + tid] : 0.0;
+            const double xn = xf + ((spart[tid] + spart[NP + tid]) + (spart[2 * NP + tid] + spart[3 * NP + tid]));
+            sxs[tid] = xn;                         // read again only after the next barriers
+            if (tid < n) a.sm[(base + t) * n + tid] = xn;
+        }
 
         // ---- 3. M = G D (row l, columns c0..c0+7) -------------------------------------------------
         {
@@ -338,7 +285,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 int launch_smoother_wide(SmootherArgs a, cudaStream_t stream) {
     constexpr int NP = 32, LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    size_t per = 6 * NP * LD + 5 * NP + 4 * NP * NP + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
+    size_t per = 6 * NP * LD + 12 * NP + 4 * NP * NP + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
     const size_t smem = (per + 2) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(smoother_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
