@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     double *scol = sm_;  sm_ += 2 * NP;    // Gauss-Jordan: column k of the current matrix (double-buffered)
     double *srow = sm_;  sm_ += 2 * NP;    // ... and its row k
     double *spart = sm_; sm_ += 4 * NP;    // partial sums of G delta, one per warp
-    double *stage = sm_; sm_ += 2 * 2 * NP * NP;   // [buffer][P_p | P_f][n*n] as they lie in global memory
+    double *stage = sm_; sm_ += 2 * 2 * NP * LD;   // [buffer][P_p | P_f][row][LD]
     double *sHp = sm_;   sm_ += (size_t)a.p * NP;  // projection matrix rows (fused epilogue)
     double *sA = sm_;                      // full A (only when not diagonal)
 
@@ -87,14 +87,24 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         }
     };
 
+    // The staged matrices keep the padded row pitch LD of the working matrices: read back row-per-lane
+    // at the global pitch n = 32 every lane would hit the same bank.
+    const int srow0 = tid / n, scol0 = tid % n, srow_inc = kSwThreads / n, scol_inc = kSwThreads % n;
     auto issue_step = [&](int64_t t, int buf) {     // inputs of backward step t: P_p[t+1], P_f[t]
         if (t >= 0) {
             const double *srcp = a.pc + (base + t + 1) * nn;
             const double *srcf = a.fc + (base + t) * nn;
-            double *dst = stage + (size_t)buf * 2 * NP * NP;
+            double *dst = stage + (size_t)buf * 2 * NP * LD;
+            int rr = srow0, cc = scol0;
             for (int i = tid; i < nn; i += kSwThreads) {
-                cp_async8(dst + i, srcp + i);
-                cp_async8(dst + NP * NP + i, srcf + i);
+                cp_async8(dst + rr * LD + cc, srcp + i);
+                cp_async8(dst + NP * LD + rr * LD + cc, srcf + i);
+                rr += srow_inc;
+                cc += scol_inc;
+                if (cc >= n) {
+                    cc -= n;
+                    ++rr;
+                }
             }
         }
         cp_async_commit();
@@ -126,13 +136,13 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         __syncthreads();
         // ---- 0. spread the staged matrices; D; delta -----------------------------------------
         {
-            const double *sp = stage + (size_t)buf * 2 * NP * NP, *sf = sp + NP * NP;
+            const double *sp = stage + (size_t)buf * 2 * NP * LD, *sf = sp + NP * LD;
 #pragma unroll
             for (int c = 0; c < PW; ++c) {
                 const int cc = c0 + c;
                 const bool in = l < n && cc < n;
-                const double pp = in ? sp[l * n + cc] : ((l == cc) ? 1.0 : 0.0);   // padding: identity
-                const double pf = in ? sf[l * n + cc] : 0.0;
+                const double pp = in ? sp[l * LD + cc] : ((l == cc) ? 1.0 : 0.0);   // padding: identity
+                const double pf = in ? sf[l * LD + cc] : 0.0;
                 sL[l * LD + cc] = pp;
                 if (l == cc) sdg[l] = pp;
                 sPf[l * LD + cc] = pf;
@@ -150,8 +160,9 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         // pivot, 8 FMAs per thread, no triangular solves afterwards -- the blocked Cholesky with its
         // redundant 8 x 8 factorisations, three barriers per panel and 64 dependent substitution steps per
         // right-hand side (four lanes per column, a shuffle per step) cost three times as much.
-        double dmax = 0.0;                        // largest diagonal entry: scale of pinv's cut-off
-        for (int i = 0; i < n; ++i) dmax = fmax(dmax, sdg[i]);
+        double dmax = (l < n) ? sdg[l] : 0.0;     // largest diagonal entry: scale of pinv's cut-off
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, off));
         double pr[PW];
 #pragma unroll
         for (int c = 0; c < PW; ++c) pr[c] = sL[l * LD + c0 + c];
@@ -169,19 +180,18 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
             const bool okp = d > 1.5e-14 * sdg[k] && d > 1e-15 * dmax && d > 0.0;
             if (!okp) status |= MKF_STATUS_CHOL_FAILED;
             const double pv = okp ? rcp_nr(d) : 0.0;
-            const double cl = colk[l];
+            // row k becomes (row k) * pv, every other row l: a_lj - (a_lk pv) a_kj; with clp = a_lk pv
+            // (= -pv in row k, whose own entries then start from zero) both are ONE fma per entry, and the
+            // entry in column k is -clp in either case
+            const bool mine = l == k;
+            const double clp = mine ? -pv : colk[l] * pv;
 #pragma unroll
             for (int c = 0; c < PW; c += 2) {
                 const double2 rk2 = *reinterpret_cast<const double2 *>(rowk + c0 + c);
-                const double rk[2] = {rk2.x * pv, rk2.y * pv};
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = c0 + c + h;
-                    const double upd = (j == k) ? -cl * pv : fma(-cl, rk[h], pr[c + h]);
-                    const double own = (j == k) ? pv : rk[h];
-                    pr[c + h] = (l == k) ? own : upd;
-                }
+                pr[c] = fma(-clp, rk2.x, mine ? 0.0 : pr[c]);
+                pr[c + 1] = fma(-clp, rk2.y, mine ? 0.0 : pr[c + 1]);
             }
+            if (w == k / PW) pr[k % PW] = -clp;
         }
 #pragma unroll
         for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2 *>(sL + l * LD + c0 + c) = make_double2(pr[c], pr[c + 1]);
@@ -190,7 +200,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
             double fr[PW];
 #pragma unroll
             for (int c = 0; c < PW; ++c) fr[c] = 0.0;
-            for (int k = 0; k < n; ++k) {
+#pragma unroll 8
+            for (int k = 0; k < NP; ++k) {          // (padding rows / columns are zero)
                 const double av = sA[l * LD + k];
 #pragma unroll
                 for (int c = 0; c < PW; c += 2) {
@@ -209,7 +220,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
             double g[PW];
 #pragma unroll
             for (int c = 0; c < PW; ++c) g[c] = 0.0;
-            for (int k = 0; k < n; ++k) {
+#pragma unroll 8
+            for (int k = 0; k < NP; ++k) {
                 const double f = diagA ? sa[k] * sPf[k * LD + l] : sM[k * LD + l];
 #pragma unroll
                 for (int c = 0; c < PW; c += 2) {
@@ -240,7 +252,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
             double Mrow[PW];
 #pragma unroll
             for (int c = 0; c < PW; ++c) Mrow[c] = 0.0;
-            for (int k = 0; k < n; ++k) {
+#pragma unroll 8
+            for (int k = 0; k < NP; ++k) {
                 const double g = sG[l * LD + k];
 #pragma unroll
                 for (int c = 0; c < PW; c += 2) {
@@ -258,7 +271,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
             double out[PW];
 #pragma unroll
             for (int c = 0; c < PW; ++c) out[c] = sPf[l * LD + c0 + c];
-            for (int k = 0; k < n; k += 2) {
+#pragma unroll 4
+            for (int k = 0; k < NP; k += 2) {
                 const double2 mk = *reinterpret_cast<const double2 *>(sM + l * LD + k);
 #pragma unroll
                 for (int c = 0; c < PW; ++c) {
@@ -285,7 +299,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 int launch_smoother_wide(SmootherArgs a, cudaStream_t stream) {
     constexpr int NP = 32, LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    size_t per = 6 * NP * LD + 12 * NP + 4 * NP * NP + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
+    size_t per = 6 * NP * LD + 12 * NP + 4 * NP * LD + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
     const size_t smem = (per + 2) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(smoother_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py tests/test_gpu_host.py -m gpu -x -q -k "smooth or c3 or wide or n32 or n20 or run_smoother or simul or decompose" 2>&1 | tail -4
+timeout 600 python tests/probe_c3.py 2>&1 | head -2 | tee gpurun_out/r02r_probe_c3.txt
