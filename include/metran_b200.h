@@ -210,7 +210,7 @@ int mkf_smoother_project(int64_t B, int64_t T, int32_t n,
  * mkf_smoother runs batches of at least `min_batch` diagonal-A models with n = 4 or n = 8 on the
  * thread-per-model kernel (TMA-staged inputs and outputs; needs 16-byte aligned arrays), everything else
  * on the lane-per-row / four-warp kernels.  mkf_smoother_set_thread_min_batch sets that threshold (default
- * 2048; negative = default) and returns the previous one; mkf_dfm_set_hist_tma(0) disables the kernel
+ * 6144; negative = default) and returns the previous one; mkf_dfm_set_hist_tma(0) disables the kernel
  * altogether.  Same results to rounding (used by the parity tests).  No reference counterpart.
  */
 int64_t mkf_smoother_set_thread_min_batch(int64_t min_batch);

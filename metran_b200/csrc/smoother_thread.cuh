@@ -39,11 +39,16 @@ struct SmThreadMaps {
 };
 
 #ifndef MKF_SMT_MIN_B
-#define MKF_SMT_MIN_B 2048      // below this the lane-per-row kernel has more warps to hide latency with
+#define MKF_SMT_MIN_B 6144      // below this the lane-per-row kernel is faster: more warps to hide latency with
+                                // (measured crossover between 4096 and 8192 models, profiles/r02t_smoother8.txt)
 #endif
 std::atomic<long long> g_smt_min_b{MKF_SMT_MIN_B};
 inline int64_t smoother_thread_min_b() { return (int64_t)g_smt_min_b.load(); }
-constexpr int kSmtTSM = 4;      // steps per tensor store of the smoothed means
+#ifndef MKF_SMT_LEAN
+#define MKF_SMT_LEAN 1          // 1: P_f / x_f / x_p single-buffered, x_s boxes of 2 steps, n - 1 gain rows kept:
+#endif                          //    73 KB instead of 101 KB per 32 models = three CTAs (six warps) per SM
+constexpr bool kSmtLean = MKF_SMT_LEAN != 0;
+constexpr int kSmtTSM = kSmtLean ? 2 : 4;      // steps per tensor store of the smoothed means
 
 template <int N>
 struct SmtLayout {
@@ -52,11 +57,12 @@ struct SmtLayout {
     static constexpr unsigned MEAN = 32u * N * 8u;        // one mean box (one step)
     // offsets from the 1 KB aligned base
     static constexpr unsigned PC = 0;
-    static constexpr unsigned FC0 = PC + COV, FC1 = FC0 + COV;
+    static constexpr unsigned FC0 = PC + COV, FC1 = kSmtLean ? FC0 : FC0 + COV;
     static constexpr unsigned SC = FC1 + COV;
     static constexpr unsigned G = SC + COV;                // gain rows [c][lane][N], N*8-byte swizzle
-    static constexpr unsigned GBYTES = N * MEAN;
-    static constexpr unsigned PM0 = G + GBYTES, PM1 = PM0 + MEAN, FM0 = PM1 + MEAN, FM1 = FM0 + MEAN;
+    static constexpr unsigned GBYTES = (kSmtLean ? N - 1 : N) * MEAN;   // (the last row is never read back)
+    static constexpr unsigned PM0 = G + GBYTES, PM1 = kSmtLean ? PM0 : PM0 + MEAN;
+    static constexpr unsigned FM0 = PM1 + MEAN, FM1 = kSmtLean ? FM0 : FM0 + MEAN;
     static constexpr unsigned SMO = FM1 + MEAN;            // smoothed means, kSmtTSM steps
     static constexpr unsigned AD = SMO + kSmtTSM * MEAN;   // diag(A) [i][lane]
     static constexpr unsigned BARS = AD + N * 32u * 8u;    // mbarriers: pc, stage 0, stage 1
@@ -76,7 +82,7 @@ __device__ __forceinline__ void smt_static_for(F &&f) {
 #endif
 
 template <int N>
-__global__ void __launch_bounds__(32 * MKF_SMT_WARPS, 2) smoother_thread_kernel(const SmootherArgs a, const __grid_constant__ SmThreadMaps maps) {
+__global__ void __launch_bounds__(32 * MKF_SMT_WARPS, MKF_SMT_LEAN ? 3 : 2) smoother_thread_kernel(const SmootherArgs a, const __grid_constant__ SmThreadMaps maps) {
     using LY = SmtLayout<N>;
     constexpr int NT = N * (N + 1) / 2;
     constexpr int NW = MKF_SMT_WARPS;
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(32 * MKF_SMT_WARPS, 2) smoother_thread_kernel(
     };
     // loads of one backward step t: P_f[t], x_f[t], x_p[t+1] into stage (t & 1); P_p[t+1] separately
     auto issue_stage = [&](int64_t t) {
-        const unsigned s = (unsigned)(t & 1), bar = s ? bar_st1 : bar_st0;
+        const unsigned s = kSmtLean ? 0u : (unsigned)(t & 1), bar = s ? bar_st1 : bar_st0;
         expect(bar, LY::COV + 2u * LY::MEAN);
         load3d(base + (s ? LY::FC1 : LY::FC0), &maps.fc, (int)t * LY::LINES, bar);
         load3d(base + (s ? LY::FM1 : LY::FM0), &maps.fm, (int)t, bar);
@@ -177,17 +183,17 @@ __global__ void __launch_bounds__(32 * MKF_SMT_WARPS, 2) smoother_thread_kernel(
     // P_f[T-1] and x_f[T-1] are fetched as "stage T-1" (the x_p box of that stage is not used)
     unsigned ph_pc = 0, ph_st0 = 0, ph_st1 = 0;
     if (leader) {
-        const unsigned s = (unsigned)((T - 1) & 1), bar = s ? bar_st1 : bar_st0;
+        const unsigned s = kSmtLean ? 0u : (unsigned)((T - 1) & 1), bar = s ? bar_st1 : bar_st0;
         expect(bar, LY::COV + LY::MEAN);
         load3d(base + (s ? LY::FC1 : LY::FC0), &maps.fc, (int)(T - 1) * LY::LINES, bar);
         load3d(base + (s ? LY::FM1 : LY::FM0), &maps.fm, (int)(T - 1), bar);
         if (T >= 2) {
-            issue_stage(T - 2);
+            if (!kSmtLean) issue_stage(T - 2);
             issue_pc(T - 2);
         }
     }
     {
-        const unsigned s = (unsigned)((T - 1) & 1);
+        const unsigned s = kSmtLean ? 0u : (unsigned)((T - 1) & 1);
         bar_wait(s ? bar_st1 : bar_st0, 0u);
         if (s) ph_st1 ^= 1u; else ph_st0 ^= 1u;
         const unsigned fcb = base + (s ? LY::FC1 : LY::FC0), fmb = base + (s ? LY::FM1 : LY::FM0);
@@ -216,15 +222,17 @@ __global__ void __launch_bounds__(32 * MKF_SMT_WARPS, 2) smoother_thread_kernel(
             store3d(&maps.sc, (int)(T - 1) * LY::LINES, base + LY::SC);
             if ((T - 1) % kSmtTSM == 0) store3d(&maps.sm, (int)(T - 1), base + LY::SMO);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (kSmtLean && T >= 2) issue_stage(T - 2);     // the one stage is free again
         }
     }
 
     int status = 0;
     for (int64_t t = T - 2; t >= 0; --t) {
-        const unsigned s = (unsigned)(t & 1);
-        // stage (t - 1) & 1 == (t + 1) & 1 was read by step t + 1 (or by the prologue), which has finished
-        // -- proxy fence and barrier in front of its stores: refill it for step t - 1
-        if (leader && t >= 1) issue_stage(t - 1);
+        const unsigned s = kSmtLean ? 0u : (unsigned)(t & 1);
+        // two stages: stage (t - 1) & 1 == (t + 1) & 1 was read by step t + 1 (or by the prologue), which has
+        // finished -- proxy fence and barrier in front of its stores: refill it for step t - 1.  (One stage:
+        // refilled at the end of the step that read it; the load flies during the next step's factorisation.)
+        if (!kSmtLean && leader && t >= 1) issue_stage(t - 1);
 
         // ---- P_p[t+1] -> registers; D = P_s[t+1] - P_p[t+1] (every warp: all of it) --------------------
         bar_wait(bar_pc, ph_pc);
@@ -343,8 +351,10 @@ __global__ void __launch_bounds__(32 * MKF_SMT_WARPS, 2) smoother_thread_kernel(
                     }
                     g[i] = acc;
                 }
+                if (!kSmtLean || C < N - 1) {
 #pragma unroll
-                for (int i = 0; i < N; i += 2) sts2(vec_pair(base + LY::G + (unsigned)C * LY::MEAN, i), g[i], g[i + 1]);
+                    for (int i = 0; i < N; i += 2) sts2(vec_pair(base + LY::G + (unsigned)C * LY::MEAN, i), g[i], g[i + 1]);
+                }
             };
             auto row_tail = [&](auto cc) {
                 constexpr int C = decltype(cc)::value;
@@ -413,6 +423,7 @@ __global__ void __launch_bounds__(32 * MKF_SMT_WARPS, 2) smoother_thread_kernel(
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         cta_sync();
         if (leader) {
+            if (kSmtLean && t >= 1) issue_stage(t - 1);
             store3d(&maps.sc, (int)t * LY::LINES, base + LY::SC);
             if (t % kSmtTSM == 0) store3d(&maps.sm, (int)t, base + LY::SMO);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");

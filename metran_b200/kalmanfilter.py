@@ -450,17 +450,22 @@ class SPKalmanFilter:
         nsdf = self.observation_matrix.shape[0]
         ncdf = self.observation_matrix.shape[1] - nsdf
         eng = self._device_engine()
-        # sdf: project with the specific block only; cdf k: rank-one outer products
-        Hsdf = np.zeros_like(Hs)
-        Hsdf[:, :nsdf] = Hs[:, :nsdf]
-        sdf, _ = eng.project(means[None], None, Hsdf, variances=False)
-        sdf_means = list(sdf[0].cpu().numpy())
-        cdf_means = []
+        # one projection launch for all 1 + ncdf components: the projection matrices (specific block only;
+        # one common factor each) are stacked row-wise and the result is split again
+        p = Hs.shape[0]
+        stack = np.zeros(((1 + ncdf) * p, Hs.shape[1]))
+        stack[:p, :nsdf] = Hs[:, :nsdf]
         for k in range(ncdf):
-            Hk = np.zeros_like(Hs)
-            Hk[:, nsdf + k] = Hs[:, nsdf + k]
-            ck, _ = eng.project(means[None], None, Hk, variances=False)
-            cdf_means.append(list(ck[0].cpu().numpy()))
+            stack[(1 + k) * p:(2 + k) * p, nsdf + k] = Hs[:, nsdf + k]
+        if stack.shape[0] <= 256:
+            allc, _ = eng.project(means[None], None, stack, variances=False)
+            allc = allc[0].cpu().numpy()                     # [T, (1 + ncdf) * p]
+            parts = [allc[:, i * p:(i + 1) * p] for i in range(1 + ncdf)]
+        else:                                                # beyond mkf_project's width: one launch per component
+            parts = [eng.project(means[None], None, stack[i * p:(i + 1) * p], variances=False)[0][0].cpu().numpy()
+                     for i in range(1 + ncdf)]
+        sdf_means = list(parts[0])
+        cdf_means = [list(c) for c in parts[1:]]
         return (sdf_means, cdf_means)
 
     # ---------------------------------------------------------------------- internals

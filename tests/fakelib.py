@@ -208,7 +208,7 @@ class FakeLib:
         return 1
 
     def mkf_smoother_set_thread_min_batch(self, min_batch):
-        return 2048
+        return 6144
 
     # ---- smoother / projections / reduction ---------------------------------------------
     def mkf_smoother(self, B, T, n, fm, fc, pm, pc, A, As, flags, sm, sc, status, stream):

@@ -4,9 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    # thread-per-model smoother: warps that share one set of boxes
-    "smt_w1": ["-DMKF_SMT_WARPS=1"],
-    "smt_w4": ["-DMKF_SMT_WARPS=4"],
+    # thread-per-model smoother: the 101 KB layout (double-buffered P_f, 4-step x_s boxes), 2 CTAs per SM
+    "smt_full": ["-DMKF_SMT_LEAN=0"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}

@@ -19,7 +19,7 @@ for path in [None] + libs:
     if path is not None:
         eng.lib = _lib.load(path)
     for thread_kernel in (1, 0):
-        prev = eng.lib.mkf_smoother_set_thread_min_batch(2048 if thread_kernel else 1 << 40)
+        prev = eng.lib.mkf_smoother_set_thread_min_batch(1 if thread_kernel else 1 << 40)
         ts = []
         for _ in range(4):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
