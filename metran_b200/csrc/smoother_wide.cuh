@@ -19,10 +19,14 @@
 
 namespace {
 
-constexpr int kSwThreads = 128;
+#ifndef MKF_SW_PW
+#define MKF_SW_PW 8          // columns of a row per thread: 8 = four warps per model, 4 = eight warps
+#endif
+constexpr int kSwWarps = 32 / MKF_SW_PW;
+constexpr int kSwThreads = 32 * kSwWarps;
 
 __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const SmootherArgs a) {
-    constexpr int NP = 32, LD = NP + 2, PW = 8;       // PW: panel width = columns per warp
+    constexpr int NP = 32, LD = NP + 2, PW = MKF_SW_PW;       // PW: columns per warp
     extern __shared__ __align__(16) double smem[];
     const int n = a.n;
     const int tid = threadIdx.x, l = tid & 31, w = tid >> 5, c0 = w * PW;
@@ -42,7 +46,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     double *sdg = sm_;   sm_ += NP;        // original diagonal of P_p[t+1] (singularity test of the pivots)
     double *scol = sm_;  sm_ += 2 * NP;    // Gauss-Jordan: column k of the current matrix (double-buffered)
     double *srow = sm_;  sm_ += 2 * NP;    // ... and its row k
-    double *spart = sm_; sm_ += 4 * NP;    // partial sums of G delta, one per warp
+    double *spart = sm_; sm_ += kSwWarps * NP;    // partial sums of G delta, one per warp
     double *stage = sm_; sm_ += 2 * 2 * NP * LD;   // [buffer][P_p | P_f][row][LD]
     double *sHp = sm_;   sm_ += (size_t)a.p * NP;  // projection matrix rows (fused epilogue)
     double *sA = sm_;                      // full A (only when not diagonal)
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     auto project = [&](int64_t t) {
         if (a.p <= 0) return;
         if (a.svar && tid < n) a.svar[(base + t) * n + tid] = sPs[tid * LD + tid];
-        for (int j = w; j < a.p; j += 4) {
+        for (int j = w; j < a.p; j += kSwWarps) {
             const double *h = sHp + j * NP;
             double u = 0.0;
 #pragma unroll
@@ -242,7 +246,10 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         __syncthreads();
         if (tid < NP) {
             const double xf = (tid < n) ? a.fm[(base + t) * n + tid] : 0.0;
-            const double xn = xf + ((spart[tid] + spart[NP + tid]) + (spart[2 * NP + tid] + spart[3 * NP + tid]));
+            double xg = (spart[tid] + spart[NP + tid]) + (spart[2 * NP + tid] + spart[3 * NP + tid]);
+            if (kSwWarps == 8)
+                xg += (spart[4 * NP + tid] + spart[5 * NP + tid]) + (spart[6 * NP + tid] + spart[7 * NP + tid]);
+            const double xn = xf + xg;
             sxs[tid] = xn;                         // read again only after the next barriers
             if (tid < n) a.sm[(base + t) * n + tid] = xn;
         }
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 int launch_smoother_wide(SmootherArgs a, cudaStream_t stream) {
     constexpr int NP = 32, LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    size_t per = 6 * NP * LD + 12 * NP + 4 * NP * LD + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
+    size_t per = 6 * NP * LD + (8 + kSwWarps) * NP + 4 * NP * LD + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
     const size_t smem = (per + 2) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(smoother_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
