@@ -185,6 +185,296 @@ __host__ __device__ __forceinline__ void collapsed_step(double *x, double *P, co
     collapsed_step_impl<M, K, false>(x, P, phi, qc, yp, yv, ld, [](int, double) {}, sigma, stepprod, bad);
 }
 
+// ---- information form of the same step ------------------------------------------------------------
+// The elimination above works on the (M + K) x (M + K) joint matrix [S T^T; T C-] with M pivots.  The
+// same step can be taken in the K x K factor space (K <= 3 < M for Metran): with S0 = L0 L0^T,
+//     vt = L0^-1 v = L0^-1 z + Dt c                 z = y - phi_s*y_prev,  Dt = L0^-1 D          (M x K)
+//     v  = -D e + eps,  e ~ N(0, C) the factor error, eps ~ N(0, S0), cov(w_c, eps) = QG
+//     N  = Dt^T Dt = R^T R  (R upper triangular),   b = Dt^T vt
+//     C' = (C^-1 + N)^-1 = C - (R C)^T (I + R C R^T)^-1 (R C)          posterior covariance of e
+//     e' = -C' b                                                        ... and its mean
+//     sigma = v^T S^-1 v = vt.vt + b.e',     det S = det S0 * det(I + R C R^T)
+//     c+ = Phi_c c + Jt vt + Ft e',   C+ = Ft C' Ft^T + Qt
+//     Jt = QG L0^-T (K x M),  Ft = Phi_c + Jt Dt (K x K),  Qt = Q_c - Jt Jt^T (K x K)
+// (w_c = Jt (vt + Dt e) + w~ with w~ independent of eps: the correlated part of the process noise is
+// known once v is).  E = I + R C R^T is K x K: K pivots instead of M, 227 instead of 312 fp64
+// instructions at (5, 3).  The pivots are NOT the reference's innovation variances any more -- only
+// sigma and det S of the whole step are reproduced (to rounding), which is all -2 log L needs; the
+// step that captures the steady-state constants (1/f_i, multipliers, gains) is taken in the
+// elimination form.
+// Constants: [L0^-1 (packed lower, M(M+1)/2)] [Dt (M*K)] [Jt (K*M)] [R (packed upper, K(K+1)/2)]
+//            [Ft (K*K)] [Qt (packed upper, K(K+1)/2)] [det S0].
+__host__ __device__ constexpr int collapsed_info_const_count(int M, int K) {
+    return M * (M + 1) / 2 + 2 * M * K + K * (K + 1) + K * K + 1;
+}
+// the M-sized part (L0^-1, Dt, Jt): same size as the elimination form's constants
+__host__ __device__ constexpr int collapsed_info_smem_count(int M, int K) { return M * (M + 1) / 2 + 2 * M * K; }
+template <int N>
+__host__ __device__ constexpr int ltri(int r, int c) {   // packed lower triangle, c <= r
+    return r * (r + 1) / 2 + c;
+}
+
+template <int M, int K, class Store>
+__host__ __device__ __forceinline__ void collapsed_info_consts(const double *phi, const double *q, const double *G,
+                                                               Store store) {
+    constexpr int ML = M * (M + 1) / 2, KT = K * (K + 1) / 2;
+    // S0 = Gamma Q_c Gamma^T + Q_s (lower), D, QG
+    double L[ML], D[M * K], QG[K * M];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int l = 0; l <= i; ++l) {
+            double s = (i == l) ? q[i] : 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) s = fma(G[i * K + j] * q[M + j], G[l * K + j], s);
+            L[ltri<M>(i, l)] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            D[i * K + j] = G[i * K + j] * (phi[i] - phi[M + j]);
+            QG[j * M + i] = q[M + j] * G[i * K + j];
+        }
+    // Cholesky S0 = L0 L0^T in place, then W = L0^-1 in place (S0 is positive definite: q_s > 0)
+    double inv[M], det = 1.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        const double pjj = L[ltri<M>(j, j)];
+        det *= pjj;
+        const double iv = 1.0 / sqrt(pjj);
+        inv[j] = iv;
+#pragma unroll
+        for (int r = j + 1; r < M; ++r) L[ltri<M>(r, j)] *= iv;
+#pragma unroll
+        for (int r = j + 1; r < M; ++r)
+#pragma unroll
+            for (int c = j + 1; c <= r; ++c) L[ltri<M>(r, c)] = fma(-L[ltri<M>(r, j)], L[ltri<M>(c, j)], L[ltri<M>(r, c)]);
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        L[ltri<M>(j, j)] = inv[j];
+#pragma unroll
+        for (int i = j + 1; i < M; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = j; k < i; ++k) acc = fma(L[ltri<M>(i, k)], L[ltri<M>(k, j)], acc);
+            L[ltri<M>(i, j)] = -inv[i] * acc;
+        }
+    }
+    // Dt = W D, Jt = QG W^T
+    double Dt[M * K], Jt[K * M];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int l = 0; l <= i; ++l) {
+                a = fma(L[ltri<M>(i, l)], D[l * K + j], a);
+                b = fma(L[ltri<M>(i, l)], QG[j * M + l], b);
+            }
+            Dt[i * K + j] = a;
+            Jt[j * M + i] = b;
+        }
+    // N = Dt^T Dt = R^T R: Cholesky of N (lower factor = R^T); a direction D does not see (rank of D
+    // below K, e.g. equal decay rates) gives a zero pivot: that row of R is zero
+    double Nl[KT];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = 0; l <= j; ++l) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) s = fma(Dt[i * K + j], Dt[i * K + l], s);
+            Nl[ltri<K>(j, l)] = s;
+        }
+    double tr = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) tr += Nl[ltri<K>(j, j)];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const double pjj = Nl[ltri<K>(j, j)];
+        const bool ok = pjj > 1e-28 * tr && pjj > 0.0;
+        const double iv = ok ? 1.0 / sqrt(pjj) : 0.0;
+        Nl[ltri<K>(j, j)] = ok ? pjj * iv : 0.0;
+#pragma unroll
+        for (int r = j + 1; r < K; ++r) Nl[ltri<K>(r, j)] *= iv;
+#pragma unroll
+        for (int r = j + 1; r < K; ++r)
+#pragma unroll
+            for (int c = j + 1; c <= r; ++c) Nl[ltri<K>(r, c)] = fma(-Nl[ltri<K>(r, j)], Nl[ltri<K>(c, j)], Nl[ltri<K>(r, c)]);
+    }
+    int o = 0;
+#pragma unroll
+    for (int i = 0; i < ML; ++i) store(o + i, L[i]);
+    o += ML;
+#pragma unroll
+    for (int i = 0; i < M * K; ++i) store(o + i, Dt[i]);
+    o += M * K;
+#pragma unroll
+    for (int i = 0; i < K * M; ++i) store(o + i, Jt[i]);
+    o += K * M;
+    // R (upper, row-major packed: (j, l), l >= j) = transpose of the lower factor
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = j; l < K; ++l) store(o + tri<K>(j, l), Nl[ltri<K>(l, j)]);
+    o += KT;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = 0; l < K; ++l) {
+            double s = (j == l) ? phi[M + j] : 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) s = fma(Jt[j * M + i], Dt[i * K + l], s);
+            store(o + j * K + l, s);
+        }
+    o += K * K;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = j; l < K; ++l) {
+            double s = (j == l) ? q[M + j] : 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) s = fma(-Jt[j * M + i], Jt[l * M + i], s);
+            store(o + tri<K>(j, l), s);
+        }
+    o += KT;
+    store(o, det);
+}
+
+// One fully observed step in information form; same in/out contract as collapsed_step_impl (x[M..N) = c,
+// P[cc block] = C).  stepprod is multiplied by det S.
+template <int M, int K, class Load>
+__host__ __device__ __forceinline__ void collapsed_info_step(double *x, double *P, const double *phi, const double *yp,
+                                                             const double *yv, Load ld, double &sigma, double &stepprod,
+                                                             bool &bad) {
+    constexpr int N = M + K;
+    constexpr int ML = M * (M + 1) / 2, KT = K * (K + 1) / 2;
+    constexpr int oD = ML, oJ = oD + M * K, oR = oJ + K * M, oF = oR + KT, oQ = oF + K * K, oDet = oQ + KT;
+    // vt = L0^-1 z + Dt c
+    double z[M], vt[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) z[i] = fma(-phi[i], yp[i], yv[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double s = ld(ltri<M>(i, 0)) * z[0];
+#pragma unroll
+        for (int l = 1; l <= i; ++l) s = fma(ld(ltri<M>(i, l)), z[l], s);
+#pragma unroll
+        for (int j = 0; j < K; ++j) s = fma(ld(oD + i * K + j), x[M + j], s);
+        vt[i] = s;
+    }
+    double s0 = 0.0, b[K], jv[K];
+#pragma unroll
+    for (int i = 0; i < M; ++i) s0 = fma(vt[i], vt[i], s0);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double sb = 0.0, sj = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            sb = fma(ld(oD + i * K + j), vt[i], sb);
+            sj = fma(ld(oJ + j * M + i), vt[i], sj);
+        }
+        b[j] = sb;
+        jv[j] = sj;
+    }
+    // Gm = R C (K x K), E = I + Gm R^T (packed lower)
+    double R[KT], Gm[K * K], E[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) R[i] = ld(oR + i);
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = 0; l < K; ++l) {
+            double s = R[tri<K>(j, j)] * P[sym<N>(M + j, M + l)];
+#pragma unroll
+            for (int k = j + 1; k < K; ++k) s = fma(R[tri<K>(j, k)], P[sym<N>(M + k, M + l)], s);
+            Gm[j * K + l] = s;
+        }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = 0; l <= j; ++l) {
+            double s = (j == l) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = l; k < K; ++k) s = fma(Gm[j * K + k], R[tri<K>(l, k)], s);   // R[l][k] = 0 for k < l
+            E[ltri<K>(j, l)] = s;
+        }
+    // E = Le diag(e) Le^T; U = Le^-1 Gm; C' = C - U^T diag(1/e) U
+    double re[K], det = ld(oDet);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const double e = E[ltri<K>(j, j)];
+        bad = bad || cs_bad(e);
+        det *= e;
+        re[j] = cs_rcp(e);
+#pragma unroll
+        for (int r = j + 1; r < K; ++r) {
+            const double mlt = E[ltri<K>(r, j)] * re[j];
+#pragma unroll
+            for (int c = j + 1; c <= r; ++c) E[ltri<K>(r, c)] = fma(-mlt, E[ltri<K>(c, j)], E[ltri<K>(r, c)]);
+#pragma unroll
+            for (int l = 0; l < K; ++l) Gm[r * K + l] = fma(-mlt, Gm[j * K + l], Gm[r * K + l]);
+        }
+    }
+    stepprod *= det;
+    double Cp[KT];   // packed upper of the K x K block, index tri<K>
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = j; l < K; ++l) {
+            double s = P[tri<N>(M + j, M + l)];
+#pragma unroll
+            for (int k = 0; k < K; ++k) s = fma(-(Gm[k * K + j] * re[k]), Gm[k * K + l], s);
+            Cp[tri<K>(j, l)] = s;
+        }
+    // e' = -C' b; sigma; c+ = Phi_c c + Jt vt + Ft e'
+    double ep[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < K; ++l) s = fma(-Cp[sym<K>(j, l)], b[l], s);
+        ep[j] = s;
+    }
+    double sg = s0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) sg = fma(b[j], ep[j], sg);
+    sigma += sg;
+    double Ft[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) Ft[i] = ld(oF + i);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double s = fma(phi[M + j], x[M + j], jv[j]);
+#pragma unroll
+        for (int l = 0; l < K; ++l) s = fma(Ft[j * K + l], ep[l], s);
+        x[M + j] = s;
+    }
+    // C+ = Ft C' Ft^T + Qt
+    double Tm[K * K];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = 0; l < K; ++l) {
+            double s = Ft[j * K] * Cp[sym<K>(0, l)];
+#pragma unroll
+            for (int k = 1; k < K; ++k) s = fma(Ft[j * K + k], Cp[sym<K>(k, l)], s);
+            Tm[j * K + l] = s;
+        }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int l = j; l < K; ++l) {
+            double s = ld(oQ + tri<K>(j, l));
+#pragma unroll
+            for (int k = 0; k < K; ++k) s = fma(Tm[j * K + k], Ft[l * K + k], s);
+            P[tri<N>(M + j, M + l)] = s;
+        }
+}
+
 // Steady state.  For constant parameters the factor covariance C of consecutive fully observed
 // steps converges (Riccati iteration); once it has stopped changing, S, its LDL^T factors and
 // the gains are constants and a step is only

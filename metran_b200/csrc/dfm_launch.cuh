@@ -10,7 +10,7 @@ int launch_r(const DfmArgs &a0, cudaStream_t stream) {
     DfmArgs a = a0;
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    constexpr int TT = tile_steps(M, HIST);
+    constexpr int TT = tile_steps(M, HIST, !HASR && !HIST && info_shape(M, K));
     const bool shared_y = a.y_stride == 0;
     if (a.use_tma) {
         int rc = make_y_tensor_map(&map, a.y, shared_y ? 1 : a.B, a.T * M, shared_y ? a.T * M : a.y_stride,

@@ -130,8 +130,14 @@ constexpr bool kLookAhead = MKF_LOOKAHEAD != 0;
 #ifndef MKF_TT_ODD
 #define MKF_TT_ODD 6
 #endif
+// Information-form factor-only step (dfm_collapsed.cuh).  Its M-sized constants (L0^-1, Dt, Jt) take
+// exactly the room of the elimination form's (D, S0, QG); the K-sized ones (R, Ft, Qt, det S0: 22
+// doubles at K = 3) are loaded into registers at every entry of the factor-only loop.
+#ifndef MKF_INFO
+#define MKF_INFO 0
+#endif
 // history mode is bound by its stores and wants many resident warps: short tiles there
-__host__ __device__ constexpr int tile_steps(int M, bool hist = false) {
+__host__ __device__ constexpr int tile_steps(int M, bool hist = false, bool info = false) {
     return hist ? ((M % 2 == 1) ? 2 : 1) : ((M % 2 == 1) ? MKF_TT_ODD : ((M % 4 == 2) ? 5 : 6));
 }
 // q and the loadings live in registers when they fit (then no shared-memory copy is needed)
@@ -139,22 +145,38 @@ __host__ __device__ constexpr bool consts_in_regs(int M, int K) { return (M * K 
 __host__ __device__ constexpr int const_count(int M, int K) {
     return consts_in_regs(M, K) ? 0 : (M + K) + M * K;
 }
-// Collapsed (factor-only) dense step, dfm_collapsed.cuh: its constants D, S0, QG sit in shared
-// memory next to q / Gamma.  Enabled for the shapes whose CTA still fits 8 to an SM
-// (2 warps per SMSP at <= 255 registers): (228 KB - 8 x 1 KB reserved) / 8.
+// Collapsed (factor-only) dense step, dfm_collapsed.cuh: its constants sit in shared memory next to
+// q / Gamma.  Enabled for the shapes whose CTA still fits 8 to an SM (2 warps per SMSP at <= 255
+// registers): (228 KB - 8 x 1 KB reserved) / 8.
 #ifndef MKF_COLLAPSE
 #define MKF_COLLAPSE 1
 #endif
-__host__ __device__ constexpr int plain_warp_doubles(int M, int K) {
-    return kStages * 32 * tile_steps(M, false) * M + 32 * const_count(M, K);
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr bool fits_8_ctas(int ring_steps, int M, int K, int consts) {
+    return 128 + (kStages * 32 * ring_steps * M + 32 * const_count(M, K) + 32 * consts) * 8 + kStages * 8 <= 28160;
+}
+// the information form needs room for ITS constants and for the elimination form's (the capture step
+// of the steady-state switch and the frozen gains use that layout, in the same place)
+__host__ __device__ constexpr int info_region(int M, int K) {
+    return cmax(collapsed_info_smem_count(M, K), collapsed_const_count(M, K));
+}
+__host__ __device__ constexpr bool info_shape(int M, int K) {
+    return MKF_INFO != 0 && MKF_COLLAPSE != 0 && K >= 1 && fits_8_ctas(tile_steps(M, false, true), M, K, info_region(M, K));
 }
 __host__ __device__ constexpr bool collapse_shape(int M, int K) {
     return MKF_COLLAPSE != 0 && K >= 1 &&
-           128 + (plain_warp_doubles(M, K) + 32 * collapsed_const_count(M, K)) * 8 + kStages * 8 <= 28160;
+           (info_shape(M, K) || fits_8_ctas(tile_steps(M, false, false), M, K, collapsed_const_count(M, K)));
+}
+__host__ __device__ constexpr int collapse_region(int M, int K) {
+    return info_shape(M, K) ? info_region(M, K) : collapsed_const_count(M, K);
+}
+// (collapse: the R = 0, no-history build of a collapse-capable shape)
+__host__ __device__ constexpr int ring_steps(int M, int K, bool hist, bool collapse) {
+    return tile_steps(M, hist, collapse && !hist && info_shape(M, K));
 }
 __host__ __device__ constexpr int warp_doubles(int M, int K, bool hist = false, bool collapse = false) {
-    return kStages * 32 * tile_steps(M, hist) * M + 32 * const_count(M, K) +
-           ((collapse && collapse_shape(M, K)) ? 32 * collapsed_const_count(M, K) : 0);
+    return kStages * 32 * ring_steps(M, K, hist, collapse && collapse_shape(M, K)) * M + 32 * const_count(M, K) +
+           ((collapse && collapse_shape(M, K)) ? 32 * collapse_region(M, K) : 0);
 }
 // History staging.  Legacy: one record set [N + N*N][33] transposed through shared memory.  Shapes
 // with N*N a multiple of 16 doubles and N*8 a swizzle span (N = 4, 8) stage each lane's own record in
@@ -225,10 +247,11 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                                                             const __grid_constant__ HistMaps<HIST> hmaps) {
     constexpr int N = M + K;
     constexpr int NT = N * (N + 1) / 2;
-    constexpr int TT = tile_steps(M, HIST);
-    constexpr int PITCH = TT * M;  // doubles per model row of a tile
     // factor-only dense steps need R = 0 and no history output
     constexpr bool COLLAPSE = !HASR && !HIST && collapse_shape(M, K);
+    constexpr bool INFO = COLLAPSE && info_shape(M, K);    // ... taken in information form (dfm_collapsed.cuh)
+    constexpr int TT = tile_steps(M, HIST, INFO);
+    constexpr int PITCH = TT * M;  // doubles per model row of a tile
     constexpr int WARP_DOUBLES = warp_doubles(M, K, HIST, COLLAPSE) + (HIST ? hist_doubles(M, K) : 0);
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem_al =
@@ -312,7 +335,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
 #pragma unroll
             for (int i = 0; i < M * K; ++i) Greg[GREG ? i : 0] = G[i];
         }
-        if constexpr (COLLAPSE) collapsed_consts<M, K>(phi, q, G, [&](int i, double v) { ccs[i * 32] = v; });
+        if constexpr (COLLAPSE && !INFO) collapsed_consts<M, K>(phi, q, G, [&](int i, double v) { ccs[i * 32] = v; });
         __syncwarp();
     }
 #define MKF_QQ(i) (GREG ? qreg[GREG ? (i) : 0] : lds_f64(cst + (i) * 32))
@@ -930,6 +953,23 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 double cchk = -1.0;   // weighted sum of the entries of C at the last check
                 int nconv = 0;        // consecutive checks without change
                 volatile double Chold[KT];   // local memory on purpose: read back once per step
+                int since_chk = 0;           // INFO builds: steps since the last convergence check
+                constexpr int kInfoSmem = collapsed_info_smem_count(M, K);
+                double kreg[INFO ? collapsed_info_const_count(M, K) - kInfoSmem : 1];   // R, Ft, Qt, det S0
+                if constexpr (INFO) {
+                    // the constants of the information form (the region holds the elimination form's after a
+                    // capture): once per entry of this loop, i.e. once per run of fully observed steps
+                    double qq[N], gg[M * K];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) qq[i] = MKF_QQ(i);
+#pragma unroll
+                    for (int i = 0; i < M * K; ++i) gg[i] = MKF_GG(i);
+                    collapsed_info_consts<M, K>(phi, qq, gg, [&](int i, double v) {
+                        if (i < kInfoSmem) sts_f64(ccs + i * 32, v);
+                        else kreg[INFO ? i - kInfoSmem : 0] = v;
+                    });
+                    __syncwarp();
+                }
                 more = advance();
                 while (more) {
                     // y(t) and y(t-1) straight from the ring; across a tile boundary y(t-1) is the
@@ -948,7 +988,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                         yq[i] = (tt > 0) ? prev : yv[i];
                     }
                     if (!__all_sync(0xffffffffu, all_obs != 0u)) {
-                        if (kFreeze && frozen) {
+                        if (kFreeze && frozen && !INFO) {
                             // S0 and QG were overwritten by the frozen gains: put them back
                             double qq[N], gg[M * K];
 #pragma unroll
@@ -972,6 +1012,28 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                         double qc[K];
 #pragma unroll
                         for (int j = 0; j < K; ++j) qc[j] = MKF_QQ(M + j);
+                        if constexpr (INFO) {
+                            // ordinary steps in information form; the one step that captures the steady-state
+                            // constants (capture_next is warp-uniform) in the elimination form, whose D, S0, QG
+                            // replace the information-form constants first
+                            if (kFreeze && capture_next) {
+                                double qq[N], gg[M * K];
+#pragma unroll
+                                for (int i = 0; i < N; ++i) qq[i] = MKF_QQ(i);
+#pragma unroll
+                                for (int i = 0; i < M * K; ++i) gg[i] = MKF_GG(i);
+                                collapsed_consts<M, K>(phi, qq, gg, [&](int i, double v) { sts_f64(ccs + i * 32, v); });
+                                __syncwarp();
+                                collapsed_step_impl<M, K, true>(
+                                    x, P, phi, qc, yq, yc, [&](int i) { return lds_f64(ccs + i * 32); },
+                                    [&](int i, double v) { sts_f64(ccs + (M * K + i) * 32, v); }, sigma, stepprod, bad);
+                            } else {
+                                collapsed_info_step<M, K>(
+                                    x, P, phi, yq, yc,
+                                    [&](int i) { return i < kInfoSmem ? lds_f64(ccs + i * 32) : kreg[INFO ? i - kInfoSmem : 0]; },
+                                    sigma, stepprod, bad);
+                            }
+                        } else {
 #if MKF_CAPTURE_SPLIT
                         // the one step that stores its reciprocal pivots, multipliers and gains over S0 / QG
                         // (capture_next is warp-uniform) is a separate copy of the code: the 30 stores and
@@ -995,6 +1057,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                             },
                             sigma, stepprod, bad);
 #endif
+                        }
                         if (kFreeze) {
                             if (lane_holds) {
 #pragma unroll
@@ -1008,7 +1071,8 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                                 frozen = true;
                                 handoff_now = true;
                                 capture_next = false;
-                            } else if (MKF_FREEZE_EVERY_STEP || tt == 0) {
+                            } else if (INFO ? (++since_chk == 6) : (MKF_FREEZE_EVERY_STEP || tt == 0)) {
+                                since_chk = 0;
                                 // once per tile: a weighted sum of the entries of C (weights without
                                 // simple ratios, so that opposite drifts do not cancel) must not have
                                 // moved by more than 2^-50 of itself over two consecutive tiles

@@ -7,6 +7,8 @@
 // use_collapse: 0 = full-state recursion only (the kernel's general path, structured updates),
 //               1 = + factor-only step in runs of fully observed steps,
 //               3 = + steady-state switch (convergence monitor, hold, capture, data-only step).
+//               bit 2 (5, 7) = the ordinary factor-only steps in information form (collapsed_info_step);
+//               the capture step stays in the elimination form.
 // n_collapsed returns the number of factor-only steps (modes 0, 1) or of steady-state steps (3).
 #include <math.h>
 #include <stdint.h>
@@ -24,6 +26,10 @@ static double run(int64_t T, const double *y, const double *phi, const double *q
     constexpr int NT = N * (N + 1) / 2;
     double cst[collapsed_const_count(M, K) + 1];
     collapsed_consts<M, K>(phi, q, G, [&](int i, double v) { cst[i] = v; });
+    const bool info = (use_collapse & 4) != 0;
+    use_collapse &= 3;
+    double ics[collapsed_info_const_count(M, K) + 1];
+    collapsed_info_consts<M, K>(phi, q, G, [&](int i, double v) { ics[i] = v; });
     double x[N], P[NT];
     for (int i = 0; i < N; ++i) x[i] = 0.0;
     for (int r = 0; r < N; ++r)
@@ -67,7 +73,10 @@ static double run(int64_t T, const double *y, const double *phi, const double *q
                 frozen = true;
                 capture_next = false;
             } else {
-                collapsed_step<M, K>(x, P, phi, q + M, yp, yv, [&](int i) { return cst[i]; }, sigma, stepprod, bad);
+                if (info)
+                    collapsed_info_step<M, K>(x, P, phi, yp, yv, [&](int i) { return ics[i]; }, sigma, stepprod, bad);
+                else
+                    collapsed_step<M, K>(x, P, phi, q + M, yp, yv, [&](int i) { return cst[i]; }, sigma, stepprod, bad);
                 if (use_collapse != 3) ++*n_collapsed;
                 if (use_collapse == 3 && ++since_check == kCheckEvery) {
                     // the kernel's test (there: once per tile and for all lanes of the warp)

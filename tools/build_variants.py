@@ -4,8 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from metran_b200 import build
 VARIANTS = {
-    # wide smoother: eight warps per model (4 columns of a row per thread)
-    "sw_pw4": ["-DMKF_SW_PW=4"],
+    # transient kernel: factor-only steps in information form
+    "info": ["-DMKF_INFO=1"],
 }
 if len(sys.argv) > 1:
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in sys.argv[1:]}
