@@ -148,3 +148,15 @@ def test_unaligned_and_missing_outputs(eng, off):
         _call_raw(eng, y, phi, q, G, view)
         for key in keys:
             assert torch.equal(view[key], ref[key].reshape(-1)), (keys, key)
+
+
+def test_tensor_stores_on_a_batch_of_many_ctas(eng):
+    """A batch that fills the GPU several CTAs deep (three per SM resident, more waiting): every element of
+    every array equals the transposition path's."""
+    rng = np.random.default_rng(404)
+    B, T, m, k = 20000, 20, 5, 3
+    y, phi, q, G = _batch(rng, B, T, m, k, 0.1)
+    a = _run(eng, True, y, phi, q, G)
+    b = _run(eng, False, y, phi, q, G)
+    for key in KEYS:
+        assert torch.equal(a[key], b[key]), key
