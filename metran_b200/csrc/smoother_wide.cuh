@@ -11,8 +11,9 @@
 //      shared-memory matrices; D = P_s[t+1] - P_p[t+1].
 //   1. P_p^-1 in place by Gauss-Jordan elimination without pivoting: thread (w, l) keeps its 8 entries
 //      of row l in registers, column k and row k of the current matrix travel through two small
-//      double-buffered vectors -- one block barrier and 8 FMAs per thread and pivot (round 2; the
-//      blocked Cholesky + 64-step substitutions of the first version took three times as long).
+//      double-buffered vectors, two pivots per block barrier (what the first does to the second's row and
+//      column every thread works out itself): 16 barriers and 32 x 8 + 16 x 9 FMAs per thread (round 2;
+//      the blocked Cholesky + 64-step substitutions of the first version took twice as long).
 //   2. G = (A P_f)^T P_p^-1 as a 32 x 32 x 32 product with the operands in shared memory.
 //   3. x_s[t], M = G D, P_s[t] = P_f + M G^T: thread (w, l) produces row l, columns [8w, 8w+8).
 #pragma once
@@ -44,8 +45,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
     double *sa = sm_;    sm_ += NP;        // diag(A)
     double *sxs = sm_;   sm_ += NP;        // x_s[t]
     double *sdg = sm_;   sm_ += NP;        // original diagonal of P_p[t+1] (singularity test of the pivots)
-    double *scol = sm_;  sm_ += 2 * NP;    // Gauss-Jordan: column k of the current matrix (double-buffered)
-    double *srow = sm_;  sm_ += 2 * NP;    // ... and its row k
+    double *scol = sm_;  sm_ += 4 * NP;    // Gauss-Jordan: columns k, k+1 of the current matrix (double-buffered)
+    double *srow = sm_;  sm_ += 4 * NP;    // ... and its rows k, k+1
     double *spart = sm_; sm_ += kSwWarps * NP;    // partial sums of G delta, one per warp
     double *stage = sm_; sm_ += 2 * 2 * NP * LD;   // [buffer][P_p | P_f][row][LD]
     double *sHp = sm_;   sm_ += (size_t)a.p * NP;  // projection matrix rows (fused epilogue)
@@ -170,32 +171,61 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
         double pr[PW];
 #pragma unroll
         for (int c = 0; c < PW; ++c) pr[c] = sL[l * LD + c0 + c];
+        // TWO pivots per barrier: rows k, k+1 and columns k, k+1 are published as they are before pivot k;
+        // what pivot k does to row k+1 and to column k+1 every thread works out for itself (8 + 1 extra
+        // FMAs), so that pivot k+1 follows without another exchange -- the same operations on the same
+        // numbers as one pivot per round (bit-identical results), half the barriers.
 #pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            double *colk = scol + (k & 1) * NP, *rowk = srow + (k & 1) * NP;
-            if (w == k / PW) colk[l] = pr[k % PW];
-            if (l == k) {
+        for (int k = 0; k < NP; k += 2) {
+            double *colk = scol + ((k >> 1) & 1) * 2 * NP, *rowk = srow + ((k >> 1) & 1) * 2 * NP;
+            if (w == k / PW) {               // (k and k + 1 belong to the same warp: PW is even)
+                colk[l] = pr[k % PW];
+                colk[NP + l] = pr[(k + 1) % PW];
+            }
+            if (l == k || l == k + 1) {
+                double *dst = rowk + (l - k) * NP + c0;
 #pragma unroll
-                for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2 *>(rowk + c0 + c) = make_double2(pr[c], pr[c + 1]);
+                for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2 *>(dst + c) = make_double2(pr[c], pr[c + 1]);
             }
             __syncthreads();
-            const double d = rowk[k];
+            // ---- pivot k.  Row k becomes (row k) * pv, every other row l: a_lj - (a_lk pv) a_kj; with
+            // clp = a_lk pv (= -pv in row k, whose own entries then start from zero) both are ONE fma per
+            // entry, and the entry in column k is -clp in either case.
+            const double d0 = rowk[k];
             // numerically singular direction: zero gain, as the reference's pinv (see smoother.cu)
-            const bool okp = d > 1.5e-14 * sdg[k] && d > 1e-15 * dmax && d > 0.0;
-            if (!okp) status |= MKF_STATUS_CHOL_FAILED;
-            const double pv = okp ? rcp_nr(d) : 0.0;
-            // row k becomes (row k) * pv, every other row l: a_lj - (a_lk pv) a_kj; with clp = a_lk pv
-            // (= -pv in row k, whose own entries then start from zero) both are ONE fma per entry, and the
-            // entry in column k is -clp in either case
-            const bool mine = l == k;
-            const double clp = mine ? -pv : colk[l] * pv;
+            const bool ok0 = d0 > 1.5e-14 * sdg[k] && d0 > 1e-15 * dmax && d0 > 0.0;
+            if (!ok0) status |= MKF_STATUS_CHOL_FAILED;
+            const double pv0 = ok0 ? rcp_nr(d0) : 0.0;
+            const bool mine0 = l == k;
+            const double clp0 = mine0 ? -pv0 : colk[l] * pv0;
+            const double c1p = colk[k + 1] * pv0;          // clp of row k + 1
+            double r1[PW];                                 // row k + 1 after pivot k, this thread's columns
 #pragma unroll
             for (int c = 0; c < PW; c += 2) {
-                const double2 rk2 = *reinterpret_cast<const double2 *>(rowk + c0 + c);
-                pr[c] = fma(-clp, rk2.x, mine ? 0.0 : pr[c]);
-                pr[c + 1] = fma(-clp, rk2.y, mine ? 0.0 : pr[c + 1]);
+                const double2 a0 = *reinterpret_cast<const double2 *>(rowk + c0 + c);
+                const double2 a1 = *reinterpret_cast<const double2 *>(rowk + NP + c0 + c);
+                pr[c] = fma(-clp0, a0.x, mine0 ? 0.0 : pr[c]);
+                pr[c + 1] = fma(-clp0, a0.y, mine0 ? 0.0 : pr[c + 1]);
+                r1[c] = fma(-c1p, a0.x, a1.x);
+                r1[c + 1] = fma(-c1p, a0.y, a1.y);
             }
-            if (w == k / PW) pr[k % PW] = -clp;
+            if (w == k / PW) {
+                pr[k % PW] = -clp0;
+                r1[k % PW] = -c1p;
+            }
+            // column k + 1 of this thread's row after pivot k, and the pivot itself
+            const double a_k_k1 = rowk[k + 1];
+            const double cl1 = fma(-clp0, a_k_k1, mine0 ? 0.0 : colk[NP + l]);
+            const double d1 = fma(-c1p, a_k_k1, rowk[NP + k + 1]);
+            // ---- pivot k + 1
+            const bool ok1 = d1 > 1.5e-14 * sdg[k + 1] && d1 > 1e-15 * dmax && d1 > 0.0;
+            if (!ok1) status |= MKF_STATUS_CHOL_FAILED;
+            const double pv1 = ok1 ? rcp_nr(d1) : 0.0;
+            const bool mine1 = l == k + 1;
+            const double clp1 = mine1 ? -pv1 : cl1 * pv1;
+#pragma unroll
+            for (int c = 0; c < PW; ++c) pr[c] = fma(-clp1, r1[c], mine1 ? 0.0 : pr[c]);
+            if (w == (k + 1) / PW) pr[(k + 1) % PW] = -clp1;
         }
 #pragma unroll
         for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2 *>(sL + l * LD + c0 + c) = make_double2(pr[c], pr[c + 1]);
@@ -306,7 +336,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) smoother_wide_kernel(const Smoo
 int launch_smoother_wide(SmootherArgs a, cudaStream_t stream) {
     constexpr int NP = 32, LD = NP + 2;
     const bool diagA = a.flags & MKF_FLAG_A_DIAGONAL;
-    size_t per = 6 * NP * LD + (8 + kSwWarps) * NP + 4 * NP * LD + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
+    size_t per = 6 * NP * LD + (12 + kSwWarps) * NP + 4 * NP * LD + (size_t)a.p * NP + (diagA ? 0 : NP * LD);
     const size_t smem = (per + 2) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(smoother_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
