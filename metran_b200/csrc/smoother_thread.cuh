@@ -14,12 +14,19 @@
 //        x_p[t+1], x_f[t] as {n, 32 models} boxes under the n*8-byte swizzle: every lane reads ITS
 //        row of the box with conflict-free 16-byte loads (the mirror image of the history kernel's
 //        stores).  P_p has one box: it is consumed at the top of the step (D, Cholesky) and the load
-//        of the next step's matrix is issued right after; P_f, x_f, x_p are double-buffered.
+//        of the next step's matrix is issued right after.  P_f, x_f, x_p: one box each, refilled at
+//        the end of the step that read them (the load flies during the next step's factorisation);
+//        MKF_SMT_LEAN=0 double-buffers them (101 KB instead of 73 KB per 32 models: two instead of
+//        three CTAs per SM, measured 16 % slower).
 //   out  P_s[t] is assembled in a box of the same layout -- which is also where the next step reads
-//        P_s[t+1] from -- and stored by one tensor store per step; x_s in boxes of 4 steps.
+//        P_s[t+1] from -- and stored by one tensor store per step; x_s in boxes of 2 steps.
 // The gain G (n x n, all of it is needed for P_f + (G D) G^T) is the one matrix that does not fit the
-// register file next to L and D: row c is written to a per-lane shared-memory row when it is solved
-// and read back by the rows after it (P_s is produced triangle-wise, row c needs G rows j <= c).
+// register file next to P_p^-1 and D: row c is written to a per-lane shared-memory row when it is
+// computed and read back by the rows after it (P_s is produced triangle-wise, row c needs G rows
+// j <= c; the last row is never read back and not stored).
+// Shared memory, not registers or bandwidth, decides how many warps an SM holds, and a lone warp runs
+// this 2700-instruction step at 0.29 IPC: MKF_SMT_WARPS = 2 warps share one set of boxes (both
+// factorise, the rows of the step alternate between them, one CTA barrier per round of rows).
 #pragma once
 #include <cuda.h>
 #include <string.h>
