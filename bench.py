@@ -199,6 +199,8 @@ def cpu_baseline(cfg, threads=0, seed=99):
     The thread count is calibrated (the GPU boxes are cgroup-limited well below their logical
     CPU count, and oversubscribing a CFS quota collapses throughput): the candidates are timed
     on the same sample and the fastest is kept and reported as `cores`."""
+    # torchrun exports OMP_NUM_THREADS=1 to its children; the CPU arm picks its own thread count
+    os.environ.pop("OMP_NUM_THREADS", None)
     from oracle import kalman_oracle as ko
 
     ko.build()
