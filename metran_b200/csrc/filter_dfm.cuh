@@ -136,6 +136,9 @@ constexpr bool kLookAhead = MKF_LOOKAHEAD != 0;
 #ifndef MKF_INFO
 #define MKF_INFO 0
 #endif
+#ifndef MKF_COMPACT_POW
+#define MKF_COMPACT_POW 1    // compacted grid: phi^k by binary powering for gaps below 256 steps (else exp(k ln phi))
+#endif
 // history mode is bound by its stores and wants many resident warps: short tiles there
 __host__ __device__ constexpr int tile_steps(int M, bool hist = false, bool info = false) {
     return hist ? ((M % 2 == 1) ? 2 : 1) : ((M % 2 == 1) ? MKF_TT_ODD : ((M % 4 == 2) ? 5 : 6));
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
             bool kstep = false;
             if constexpr (CAN_COMPACT) {
                 if (compact) {
-                    t_cur = tix[t0 + tt];
+                    t_cur = tix[t0 + tt];     // (fetching it one step ahead measured no faster: 0.374 vs 0.367 ms at C2)
                     kstep = !__all_sync(0xffffffffu, t_cur - t_prev == 1);
                 }
             }
@@ -767,11 +770,34 @@ __global__ void __launch_bounds__(kBlock) dfm_loglik_kernel(const DfmArgs a, con
                 if constexpr (CAN_COMPACT) {
                     // k = t_cur - t_prev predicts in one (k = 0 on padding steps: identity; lanes with
                     // k = 1 inside a warp that took this branch get phi^1 and q to rounding)
-                    const double kk = (double)(t_cur - t_prev);
+                    const int ki = t_cur - t_prev;
+                    const double kk = (double)ki;
                     double pk[N], qk[N];
+                    // phi^k: binary powering from phi itself while every lane's gap is short (up to 8 squarings and
+                    // 8 conditional multiplies per state: a third of the instructions of eight exp calls, and the
+                    // same rounded phi the reference multiplies by k times); exp(k ln phi) for long gaps
+                    if (MKF_COMPACT_POW && __all_sync(0xffffffffu, ki < 256)) {
+                        double bs[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            bs[i] = phi[i];
+                            pk[i] = 1.0;
+                        }
+                        const int kmax = __reduce_max_sync(0xffffffffu, ki);
+                        for (int bit = 0; (kmax >> bit) != 0; ++bit) {
+                            const bool on = ((ki >> bit) & 1) != 0;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                pk[i] = on ? pk[i] * bs[i] : pk[i];
+                                bs[i] *= bs[i];
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) pk[i] = exp(kk * lnphi[i]);
+                    }
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        pk[i] = exp(kk * lnphi[i]);
                         // 1 - phi^2k by one FMA: its ABSOLUTE error is 2^-53, times cq <= q / (1 - phi^2)
                         // (= 1 - communality or 1 for Metran) -- far below the 1e-9 contract even where the
                         // difference cancels (huge alpha), and expm1 per state and step is not free
