@@ -200,10 +200,11 @@ class KalmanEngine:
     def dfm_supported(self, m, k):
         return 1 <= m <= self.limits["dfm_m_max"] and 0 <= k <= self.limits["dfm_k_max"]
 
-    def dfm_loglik(self, y, phi, q, gamma, r=None, warmup=1):
+    def dfm_loglik(self, y, phi, q, gamma, r=None, warmup=1, out=None):
         """-2 log L of Metran-shaped models, thread-per-model kernel (mkf_dfm_loglik).
 
-        y[B,T,m] (or [T,m] shared), phi/q[B,n], gamma[B,m,k] (or shared [m,k]), r[B,m]|None.
+        y[B,T,m] (or [T,m] shared), phi/q[B,n], gamma[B,m,k] (or shared [m,k]), r[B,m]|None;
+        ``out`` = (mle[B], nobs[B] int64, status[B] int32) device tensors to reuse.
         """
         y, phi, q, gamma, r = (self.tensor(v) for v in (y, phi, q, gamma, r))
         B = self._batch((y, 2), (phi, 1), (q, 1), (gamma, 2), (r, 1))
@@ -211,9 +212,9 @@ class KalmanEngine:
         k = int(phi.shape[-1]) - m
         if gamma.shape[-2:] != (m, k):
             raise ValueError("gamma must be [.., m, k] with k = n - m")
-        mle = self.empty(B)
-        nobs = self.empty(B, dtype=torch.int64)
-        status = self.empty(B, dtype=torch.int32)
+        if out is None:
+            out = (self.empty(B), self.empty(B, dtype=torch.int64), self.empty(B, dtype=torch.int32))
+        mle, nobs, status = out
         rc = self.lib.mkf_dfm_loglik(
             B, T, m, k, _ptr(y), self._stride(y, 2), _ptr(phi), self._stride(phi, 1),
             _ptr(q), self._stride(q, 1), _ptr(gamma), self._stride(gamma, 2),

@@ -15,6 +15,7 @@ no CPU engine here: the product fails loudly without the CUDA library / a CUDA d
 from logging import getLogger
 
 import numpy as np
+import torch
 
 from . import _lib
 
@@ -509,13 +510,22 @@ class SPKalmanFilter:
         dfm = (flags == (_lib.FLAG_A_DIAGONAL | _lib.FLAG_Q_DIAGONAL) and m <= n
                and eng.dfm_supported(m, n - m) and np.array_equal(H[:, :m], np.eye(m))
                and not np.any(x0) and np.array_equal(P0, np.eye(n)))
+        if dfm:
+            # one upload for all parameters of the evaluation (phi, q, loadings, r), result buffers reused:
+            # a single model's objective call is bound by host overhead, not by the kernel
+            k = n - m
+            buf = np.concatenate([np.diag(A), np.diag(Q), np.ascontiguousarray(H[:, m:]).ravel(), R])
+            par = eng.tensor(buf)
+            phi_d, q_d = par[:n][None], par[n:2 * n][None]
+            g_d = par[2 * n:2 * n + m * k].view(1, m, k)
+            r_d = par[2 * n + m * k:][None] if np.any(R) else None
+            if getattr(self, "_out1", None) is None or self._out1[0].device != par.device:
+                self._out1 = (eng.empty(1), eng.empty(1, dtype=torch.int64), eng.empty(1, dtype=torch.int32))
         if dfm and snap.get("compact") is not None:
             yc, tidx = snap["compact"]
-            mle, _, _ = eng.dfm_loglik_compact(yc, tidx, H[:, m:][None].copy(), phi=np.diag(A)[None].copy(),
-                                               q=np.diag(Q)[None].copy(), r=R[None] if np.any(R) else None)
+            mle, _, _ = eng.dfm_loglik_compact(yc, tidx, g_d, phi=phi_d, q=q_d, r=r_d, out=self._out1)
         elif dfm:
-            mle, _, _ = eng.dfm_loglik(snap["y"], np.diag(A)[None].copy(), np.diag(Q)[None].copy(),
-                                       H[:, m:][None].copy(), r=R[None] if np.any(R) else None)
+            mle, _, _ = eng.dfm_loglik(snap["y"], phi_d, q_d, g_d, r=r_d, out=self._out1)
         else:
             mle, _, _ = eng.filter_loglik(snap["y"], A, Q, H, R, x0=x0[None], P0=P0[None], flags=flags)
         return float(mle[0])
